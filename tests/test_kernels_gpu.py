@@ -1,0 +1,154 @@
+"""Per-kernel parity on the GPU, through the C ABI, against plain PyTorch fp32 of the same op.
+
+Tolerances: operands are bf16 (rel. 2^-9), accumulation fp32. Outputs that are stored as bf16 are
+compared with atol/rtol a few bf16 ulps; fp32 outputs with the error a bf16-input GEMM must have.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from wav2vecsegmenter_b200 import _native
+
+    lib = _native.load()
+    _native.check(lib.w2vseg_device_ok(), "device_ok")
+    return lib
+
+
+def _gemm(lib, A, W, bias, act, resid, out_f32, block_n):
+    from wav2vecsegmenter_b200 import _native as n
+
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    n.check(
+        lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out),
+                        int(out_f32), block_n, n.current_stream_ptr()),
+        "gemm",
+    )
+    torch.cuda.synchronize()
+    return out
+
+
+def _ref_act(x, act):
+    if act == 1:
+        return torch.nn.functional.gelu(x)
+    if act == 2:
+        return torch.relu(x)
+    return x
+
+
+@pytest.mark.parametrize("block_n", [256, 128, 64])
+@pytest.mark.parametrize(
+    "M,N,K,act,out_f32,use_resid",
+    [
+        (128, 256, 64, 0, 1, False),      # one tile, one k-block
+        (128, 256, 256, 0, 1, False),     # one tile, several k-blocks (descriptor K advance)
+        (300, 512, 1024, 0, 1, False),    # M tail (TMA zero fill + row predicate)
+        (1000, 1024, 1024, 0, 1, True),   # residual epilogue
+        (999, 3072, 1024, 0, 0, False),   # bf16 out
+        (2000, 4096, 1024, 1, 0, False),  # GELU
+        (777, 1024, 4096, 2, 0, False),   # ReLU, long K (pipeline wrap-around)
+        (14000, 1024, 512, 0, 1, True),   # many tiles: persistent loop + TMEM double buffering
+    ],
+)
+def test_gemm(lib, M, N, K, act, out_f32, use_resid, block_n):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + act)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if use_resid else None
+    out = _gemm(lib, A, W, bias, act, resid, out_f32, block_n)
+    ref = _ref_act(A.float() @ W.float().t() + bias, act)
+    if use_resid:
+        ref = ref + resid
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-3 if out_f32 else 3e-2
+    assert err < tol, f"max abs err {err}"
+
+
+def test_gemm_inplace_residual(lib):
+    from wav2vecsegmenter_b200 import _native as n
+
+    M, N, K = 1500, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / 32).bfloat16()
+    h = torch.randn(M, N, device="cuda", generator=g)
+    ref = h + A.float() @ W.float().t()
+    n.check(lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, None, 0, n.ptr(h), n.ptr(h), 1, 256,
+                            n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert (h - ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("kw,rows_out", [(3, 1999), (2, 999), (3, 31999)])
+def test_conv_as_implicit_gemm(lib, kw, rows_out):
+    """stride-2 Conv1d over channels-last activations == GEMM over an overlapping-row TMA view"""
+    from wav2vecsegmenter_b200 import _native as n
+
+    C = 512
+    rows_in = 2 * rows_out + kw  # slack rows included
+    g = torch.Generator(device="cuda").manual_seed(kw * 100 + rows_out)
+    x = (torch.randn(rows_in, C, device="cuda", generator=g)).bfloat16()
+    w = (torch.randn(C, C, kw, device="cuda", generator=g) / math.sqrt(C * kw)).bfloat16()  # [O, I, J]
+    bias = torch.randn(C, device="cuda", generator=g)
+    wp = w.permute(0, 2, 1).contiguous().view(C, kw * C)  # K index = j*C + i
+    out = torch.empty(rows_out, C, device="cuda", dtype=torch.bfloat16)
+    n.check(lib.w2vseg_conv_gemm(n.ptr(x), rows_out, C, kw, 2, n.ptr(wp), C, n.ptr(bias), n.ptr(out),
+                                 n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv1d(x.float().t()[None], w.float(), bias, stride=2)[0].t()[:rows_out]
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("C,in_f32,act", [(1024, True, 0), (512, False, 0), (512, False, 1), (512, True, 0)])
+def test_layernorm(lib, C, in_f32, act):
+    from wav2vecsegmenter_b200 import _native as n
+
+    rows = 4099
+    g = torch.Generator(device="cuda").manual_seed(C + act)
+    x = torch.randn(rows, C, device="cuda", generator=g) * 3 + 1
+    if not in_f32:
+        x = x.bfloat16()
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = torch.empty(rows, C, device="cuda", dtype=torch.bfloat16)
+    n.check(lib.w2vseg_layernorm(n.ptr(x), int(in_f32), rows, C, n.ptr(gamma), n.ptr(beta), 1e-5, act,
+                                 n.ptr(out), n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    assert (out.float() - ref).abs().max().item() < 4e-2
+    assert (out.float() - ref).abs().mean().item() < 3e-3
+
+
+@pytest.mark.parametrize("heads,dh", [(16, 64), (8, 128)])
+@pytest.mark.parametrize("R,lens", [(1000, [999, 999]), (333, [333, 1, 200]), (130, [64, 65, 0, 130])])
+def test_attention(lib, heads, dh, R, lens):
+    from wav2vecsegmenter_b200 import _native as n
+
+    B = len(lens)
+    D = heads * dh
+    g = torch.Generator(device="cuda").manual_seed(R + dh)
+    qkv = torch.randn(B * R, 3 * D, device="cuda", generator=g).bfloat16()
+    kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    ctx = torch.empty(B * R, D, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dh)
+    n.check(lib.w2vseg_attention(n.ptr(qkv), B, R, heads, dh, n.ptr(kv_len), scale, n.ptr(ctx),
+                                 n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, R, 3, heads, dh).permute(2, 0, 3, 1, 4)  # [B, H, R, dh]
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = torch.arange(R, device="cuda")[None, :] >= kv_len[:, None]  # [B, R] keys
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)  # windows with zero valid keys -> zeros
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * R, D)
+    assert (ctx.float() - ref).abs().max().item() < 3e-2

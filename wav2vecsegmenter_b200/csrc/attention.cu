@@ -1,0 +1,281 @@
+// Fused non-causal multi-head attention with a per-window key-length mask (flash-style: S and P
+// never leave the SM; online softmax in fp32).
+//
+// Replaces Wav2Vec2Attention's softmax(QK^T*scale + mask)V (HF:500-549, 16 heads x 64) and the
+// nn.MultiheadAttention inside the head's TransformerEncoderLayer (lib/models.py:291-300, 8 x 128).
+//
+// Round-1 implementation: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) with ldmatrix
+// operand fetch from XOR-swizzled shared memory and cp.async double buffering of K/V tiles.
+// A tcgen05/TMEM version (S and O in TMEM) is the planned replacement; this one defines the
+// numerics and is the parity baseline for it.
+//
+// Layout: qkv bf16 [B*R, 3*D], D = heads*DH; Q | K | V column blocks. Window b owns rows
+// [b*R, (b+1)*R); keys t >= kv_len[b] are masked. All R rows are produced as queries.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace w2v {
+
+namespace {
+
+constexpr int ATT_BQ = 64;     // query rows per CTA (16 per warp)
+constexpr int ATT_BKV = 64;    // keys per tile
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 zero bytes written
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
+                                              uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a [rows][DH] bf16 tile, XOR-swizzled so
+// that ldmatrix (8 rows x one chunk) and the row-contiguous cp.async fills are conflict-free
+template <int DH>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  return (uint32_t)(row * (DH * 2) + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int DH>
+__device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat16* gbase,
+                                          long long ld, int row0, int rows_valid) {
+  constexpr int CHUNKS = DH / 8;
+  for (int i = threadIdx.x; i < ATT_BKV * CHUNKS; i += ATT_THREADS) {
+    const int r = i / CHUNKS, c = i - r * CHUNKS;
+    const bool ok = (row0 + r) < rows_valid;
+    const __nv_bfloat16* src = gbase + (long long)(ok ? row0 + r : 0) * ld + c * 8;
+    cp_async16(smem_base + tile_off<DH>(r, c), src, ok);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
+                 const int* __restrict__ kv_len, float scale_log2,
+                 __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  constexpr int TILE_BYTES = ATT_BKV * DH * 2;
+  const uint32_t sQ = smem_u32(att_smem);
+  const uint32_t sK = sQ + TILE_BYTES;           // 2 buffers
+  const uint32_t sV = sK + 2 * TILE_BYTES;       // 2 buffers
+
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int D = heads * DH;
+  const long long ld = 3LL * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int klen = min(kv_len[b], R);
+  const int n_tiles = (klen + ATT_BKV - 1) / ATT_BKV;
+
+  const __nv_bfloat16* gQ = qkv + (long long)b * R * ld + head * DH;
+  const __nv_bfloat16* gK = gQ + D;
+  const __nv_bfloat16* gV = gQ + 2 * D;
+
+  load_tile<DH>(sQ, gQ, ld, q0, R);
+  if (n_tiles > 0) {
+    load_tile<DH>(sK, gK, ld, 0, klen);
+    load_tile<DH>(sV, gV, ld, 0, klen);
+  }
+  cp_async_commit();
+
+  constexpr int KSTEPS = DH / 16;   // k-steps of Q K^T
+  constexpr int ONT = DH / 8;       // n-tiles of O
+  float o[ONT][4];
+#pragma unroll
+  for (int i = 0; i < ONT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  uint32_t qf[KSTEPS][4];
+  bool q_loaded = false;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_tiles) {
+      load_tile<DH>(sK + (buf ^ 1) * TILE_BYTES, gK, ld, (j + 1) * ATT_BKV, klen);
+      load_tile<DH>(sV + (buf ^ 1) * TILE_BYTES, gV, ld, (j + 1) * ATT_BKV, klen);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    if (!q_loaded) {
+      // A fragments of this warp's 16 query rows, all k-steps (kept in registers for the CTA life)
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk)
+        ldsm_x4(sQ + tile_off<DH>(r, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2],
+                qf[kk][3]);
+      q_loaded = true;
+    }
+
+    // ---- S = Q K^T for 64 keys: 8 n-tiles
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    const uint32_t kb = sK + buf * TILE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // pairs of n-tiles (16 keys)
+        const int mi = lane >> 3;
+        const int krow = np * 16 + (lane & 7) + (mi >> 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(kb + tile_off<DH>(krow, kk * 2 + (mi & 1)), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * np], qf[kk], b0, b1);
+        mma_bf16_16816(s[2 * np + 1], qf[kk], b2, b3);
+      }
+    }
+
+    // ---- mask keys beyond klen, online softmax (rows lane/4 and lane/4+8)
+    const int key0 = j * ATT_BKV + 2 * (lane & 3);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = key0 + i * 8;
+      if (k >= klen) { s[i][0] = -INFINITY; s[i][2] = -INFINITY; }
+      if (k + 1 >= klen) { s[i][1] = -INFINITY; s[i][3] = -INFINITY; }
+      mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
+    }
+    float alpha[2], moff[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      alpha[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f((m_run[r] - m_new) * scale_log2);
+      moff[r] = (m_new == -INFINITY) ? 0.f : m_new * scale_log2;
+      m_run[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float p0 = exp2f(fmaf(s[i][0], scale_log2, -moff[0]));
+      const float p1 = exp2f(fmaf(s[i][1], scale_log2, -moff[0]));
+      const float p2 = exp2f(fmaf(s[i][2], scale_log2, -moff[1]));
+      const float p3 = exp2f(fmaf(s[i][3], scale_log2, -moff[1]));
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * alpha[r] + rs[r];
+#pragma unroll
+    for (int i = 0; i < ONT; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+    }
+
+    // ---- O += P V
+    const uint32_t vb = sV + buf * TILE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < ONT / 2; ++dp) {  // pairs of d n-tiles
+        const int mi = lane >> 3;
+        const int vrow = kk * 16 + (lane & 7) + (mi & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(vb + tile_off<DH>(vrow, dp * 2 + (mi >> 1)), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], pf[kk], b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], pf[kk], b2, b3);
+      }
+    }
+    __syncthreads();  // everyone done with buf before it is refilled two iterations later
+  }
+  if (n_tiles == 0) {
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+
+  // ---- finalise: O / l, stage through this warp's rows of sQ, coalesced 16-byte stores
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = l_run[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[r] = l > 0.f ? 1.f / l : 0.f;
+  }
+  __syncwarp();
+  const int r_lo = warp * 16 + (lane >> 2);
+#pragma unroll
+  for (int i = 0; i < ONT; ++i) {
+    const int col = i * 8 + 2 * (lane & 3);
+    const uint32_t a0 = sQ + tile_off<DH>(r_lo, col >> 3) + (col & 7) * 2;
+    const uint32_t a1 = sQ + tile_off<DH>(r_lo + 8, col >> 3) + (col & 7) * 2;
+    const uint32_t v0 = pack_bf16x2(o[i][0] * inv[0], o[i][1] * inv[0]);
+    const uint32_t v1 = pack_bf16x2(o[i][2] * inv[1], o[i][3] * inv[1]);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(v0) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(v1) : "memory");
+  }
+  __syncwarp();
+  constexpr int CHUNKS = DH / 8;
+  __nv_bfloat16* gO = ctx + (long long)b * R * D + head * DH;
+  for (int i = lane; i < 16 * CHUNKS; i += 32) {
+    const int r = warp * 16 + i / CHUNKS, c = i % CHUNKS;
+    if (q0 + r < R) {
+      uint4 v;
+      const uint32_t a = sQ + tile_off<DH>(r, c);
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(a));
+      *reinterpret_cast<uint4*>(gO + (long long)(q0 + r) * D + c * 8) = v;
+    }
+  }
+}
+
+}  // namespace
+
+int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
+                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s) {
+  if (B <= 0 || R <= 0) return 0;
+  W2V_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim %d unsupported (64 / 128)",
+              head_dim);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((R + ATT_BQ - 1) / ATT_BQ, heads, B);
+  const int smem = 5 * ATT_BKV * head_dim * 2;
+  if (head_dim == 64) {
+    attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    attention_kernel<128><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
+  }
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace w2v

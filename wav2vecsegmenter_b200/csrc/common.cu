@@ -1,0 +1,121 @@
+#include "common.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+namespace w2v {
+
+namespace {
+thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+int g_num_sms = 0;
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                      uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (g_encode == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return W2VSEG_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
+    set_error("tensor map: base %p / row stride %llu not 16-byte aligned", base,
+              (unsigned long long)row_stride_elems);
+    return W2VSEG_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstride[1] = {row_stride_elems * 2};  // bytes, dim1 stride
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, box "
+              "%u x %u)",
+              (int)r, (unsigned long long)dim0, (unsigned long long)dim1,
+              (unsigned long long)row_stride_elems, box0, box1);
+    return W2VSEG_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace w2v
+
+extern "C" {
+
+int32_t w2vseg_abi_version(void) { return W2VSEG_ABI_VERSION; }
+const char* w2vseg_last_error(void) { return w2v::g_err; }
+int64_t w2vseg_launch_count(void) { return w2v::g_launches.load(std::memory_order_relaxed); }
+
+int32_t w2vseg_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    w2v::set_error("no CUDA device available");
+    return W2VSEG_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    w2v::set_error("device '%s' is sm_%d%d; libw2vseg contains sm_100a code only", prop.name,
+                   prop.major, prop.minor);
+    return W2VSEG_ERR_CUDA;
+  }
+  return 0;
+}
+
+// conv stack of wav2vec 2.0: kernels (10,3,3,3,3,2,2), strides (5,2,2,2,2,2,2), no padding
+int32_t w2vseg_num_frames(int64_t n) {
+  static const int k[7] = {10, 3, 3, 3, 3, 2, 2};
+  static const int s[7] = {5, 2, 2, 2, 2, 2, 2};
+  for (int l = 0; l < 7; ++l) {
+    if (n < k[l]) return 0;
+    n = (n - k[l]) / s[l] + 1;
+  }
+  return (int32_t)n;
+}
+
+int32_t w2vseg_frame_stride(int64_t l_max) {
+  int64_t r = (l_max + 319) / 320;
+  if (r < 2) r = 2;
+  return (int32_t)r;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Host-side plumbing shared by all translation units of libw2vseg: error reporting (no
+// exceptions cross the C ABI), the TMA tensor-map encoder (resolved through the runtime so the
+// library has no link-time dependency on libcuda), and kernel-launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/w2vseg.h"
+
+namespace w2v {
+
+void set_error(const char* fmt, ...);
+// running count of kernels launched by this library in this process (for bench accounting)
+void count_launch(int n = 1);
+
+#define W2V_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      w2v::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,        \
+                     __LINE__);                                                               \
+      return W2VSEG_ERR_CUDA;                                                                 \
+    }                                                                                         \
+  } while (0)
+
+#define W2V_CHECK_LAUNCH()                                                                    \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      w2v::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__,    \
+                     __LINE__);                                                               \
+      return W2VSEG_ERR_CUDA;                                                                 \
+    }                                                                                         \
+    w2v::count_launch();                                                                      \
+  } while (0)
+
+#define W2V_REQUIRE(cond, ...)                                                                \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      w2v::set_error(__VA_ARGS__);                                                            \
+      return W2VSEG_ERR_ARG;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+#define W2V_TRY(expr)                                                                         \
+  do {                                                                                        \
+    int _r = (expr);                                                                          \
+    if (_r != 0) return _r;                                                                   \
+  } while (0)
+
+// 2-D bf16 tensor map, 128-byte swizzle. dim0 = contiguous extent (elements), dim1 = rows,
+// row_stride_elems = distance between consecutive rows (may be SMALLER than dim0: overlapping
+// rows are how the strided convolutions are presented to the GEMM as an im2col view).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                      uint64_t row_stride_elems, uint32_t box0, uint32_t box1);
+
+int num_sms();
+
+}  // namespace w2v

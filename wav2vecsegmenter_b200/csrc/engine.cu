@@ -1,0 +1,643 @@
+// Model handle, weight packing and the forward-pass orchestration behind the C ABI (w2vseg.h).
+//
+// One handle = one SFC model replica on the current device (one process per GPU). The forward
+// pass is a fixed sequence of launches on the caller's stream; it allocates nothing and performs
+// no host synchronisation, so the host can capture it into a CUDA graph or run it ahead.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace w2v;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int kConvK[7] = {10, 3, 3, 3, 3, 2, 2};
+constexpr int kHalo = 64;  // pos-conv padding (128 // 2, HF:343)
+
+struct LNW { float* g = nullptr; float* b = nullptr; };
+
+struct EncLayerW {
+  LNW ln1, ln2;
+  bf16* wqkv = nullptr; float* bqkv = nullptr;
+  bf16* wo = nullptr;   float* bo = nullptr;
+  bf16* w1 = nullptr;   float* b1 = nullptr;   // [F1, D]: FFN-up rows, then adapter-down rows
+  bf16* w2 = nullptr;                          // [D, F1]: FFN-down cols, then scale*adapter-up cols
+  float* b2_raw = nullptr; float* bu_raw = nullptr; float* b2 = nullptr;
+  int F1 = 0;
+  bool adapter = false;
+};
+
+struct HeadW {
+  LNW ln1, ln2, lnf;
+  bf16* win = nullptr; float* bin = nullptr;
+  bf16* wo = nullptr;  float* bo = nullptr;
+  bf16* w1 = nullptr;  float* b1 = nullptr;
+  bf16* w2 = nullptr;  float* b2 = nullptr;
+  float* wout = nullptr; float* bout = nullptr;
+};
+
+enum SlotKind { SLOT_VEC, SLOT_MAT, SLOT_CONV, SLOT_CONV0, SLOT_RAW };
+
+struct Slot {
+  SlotKind kind;
+  int64_t numel;
+  // VEC / RAW
+  float* fdst = nullptr;
+  float scale = 1.f;
+  // MAT
+  bf16* bdst = nullptr;
+  int rows = 0, cols = 0;
+  int64_t ld = 0;
+  // CONV [O, I, J]
+  int O = 0, I = 0, J = 0;
+  bool optional = false;
+  int alt_group = 0;  // slots sharing a non-zero alt_group: group satisfied by its 'primary' set
+};
+
+struct Workspace {
+  float2* stats; int32_t* enc_len;
+  bf16* conv[7];
+  bf16* feat; float* h; bf16* zpad; bf16* xn; bf16* qkv; bf16* ctx; bf16* mid;
+  size_t bytes;
+};
+
+}  // namespace
+
+struct w2vseg_handle {
+  w2vseg_config cfg;
+  int D, DH, F1max;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  // weights
+  float* conv0_wt = nullptr;
+  float* conv_b[7] = {};
+  LNW conv_ln[7];
+  bf16* conv_w[7] = {};
+  LNW fp_ln; bf16* fp_w = nullptr; float* fp_b = nullptr;
+  float* pos_g = nullptr; float* pos_v = nullptr; float* pos_scale = nullptr;
+  bf16* pos_w = nullptr; float* pos_b = nullptr;
+  std::vector<EncLayerW> enc;
+  HeadW head;
+  std::map<std::string, Slot> slots;
+  std::map<std::string, bool> was_set;
+  bool finalized = false;
+
+  template <typename T>
+  T* alloc(size_t n) {
+    size_t off = (arena_used + 255) & ~(size_t)255;
+    arena_used = off + n * sizeof(T);
+    if (arena == nullptr) return nullptr;  // sizing pass
+    return reinterpret_cast<T*>(arena + off);
+  }
+};
+
+namespace {
+
+void add_vec(w2vseg_handle* h, const std::string& name, float** dst, int n, bool optional = false) {
+  *dst = h->alloc<float>(n);
+  Slot s; s.kind = SLOT_VEC; s.numel = n; s.fdst = *dst; s.optional = optional;
+  h->slots[name] = s;
+}
+void add_ln(w2vseg_handle* h, const std::string& prefix, LNW* ln, int n) {
+  add_vec(h, prefix + ".weight", &ln->g, n);
+  add_vec(h, prefix + ".bias", &ln->b, n);
+}
+// matrix [rows, cols] packed into dst (+col offset / row offset already applied), leading dim ld
+void add_mat(w2vseg_handle* h, const std::string& name, bf16* dst, int rows, int cols, int64_t ld,
+             float scale = 1.f) {
+  Slot s; s.kind = SLOT_MAT; s.numel = (int64_t)rows * cols; s.bdst = dst; s.rows = rows;
+  s.cols = cols; s.ld = ld; s.scale = scale;
+  h->slots[name] = s;
+}
+
+// Lays out every parameter in the arena and registers its upload slot. Called twice: once with
+// arena == nullptr to size the arena, once for real.
+void build_layout(w2vseg_handle* h) {
+  const w2vseg_config& c = h->cfg;
+  const int D = h->D, CD = c.conv_dim;
+  h->arena_used = 0;
+  h->slots.clear();
+
+  // feature extractor
+  h->conv0_wt = h->alloc<float>((size_t)10 * CD);
+  {
+    Slot s; s.kind = SLOT_CONV0; s.numel = (int64_t)CD * 10; s.fdst = h->conv0_wt; s.O = CD; s.J = 10;
+    h->slots["fe.conv0.weight"] = s;
+  }
+  for (int l = 0; l < 7; ++l) {
+    const std::string p = "fe.conv" + std::to_string(l);
+    add_vec(h, p + ".bias", &h->conv_b[l], CD);
+    add_ln(h, p + ".ln", &h->conv_ln[l], CD);
+    if (l > 0) {
+      h->conv_w[l] = h->alloc<bf16>((size_t)CD * CD * kConvK[l]);
+      Slot s; s.kind = SLOT_CONV; s.numel = (int64_t)CD * CD * kConvK[l]; s.bdst = h->conv_w[l];
+      s.O = CD; s.I = CD; s.J = kConvK[l];
+      h->slots[p + ".weight"] = s;
+    }
+  }
+  // feature projection
+  add_ln(h, "fp.ln", &h->fp_ln, CD);
+  h->fp_w = h->alloc<bf16>((size_t)D * CD);
+  add_mat(h, "fp.proj.weight", h->fp_w, D, CD, CD);
+  add_vec(h, "fp.proj.bias", &h->fp_b, D);
+  // positional conv: either (weight_g, weight_v) or an already folded weight
+  const int gc = D / c.pos_groups;  // channels per group
+  h->pos_g = h->alloc<float>(c.pos_kernel);
+  h->pos_v = h->alloc<float>((size_t)D * gc * c.pos_kernel);
+  h->pos_scale = h->alloc<float>(c.pos_kernel);
+  h->pos_w = h->alloc<bf16>((size_t)D * gc * c.pos_kernel);
+  {
+    Slot s; s.kind = SLOT_RAW; s.numel = c.pos_kernel; s.fdst = h->pos_g; s.alt_group = 1;
+    h->slots["pos.weight_g"] = s;
+    Slot v; v.kind = SLOT_RAW; v.numel = (int64_t)D * gc * c.pos_kernel; v.fdst = h->pos_v;
+    v.alt_group = 1;
+    h->slots["pos.weight_v"] = v;
+    Slot w; w.kind = SLOT_CONV; w.numel = v.numel; w.bdst = h->pos_w; w.O = D; w.I = gc;
+    w.J = c.pos_kernel; w.alt_group = 2;
+    h->slots["pos.weight"] = w;
+  }
+  add_vec(h, "pos.bias", &h->pos_b, D);
+
+  // encoder layers
+  h->enc.assign(c.n_layers, EncLayerW());
+  for (int i = 0; i < c.n_layers; ++i) {
+    EncLayerW& L = h->enc[i];
+    const std::string p = "enc." + std::to_string(i);
+    L.adapter = i >= c.n_layers - c.n_adapter_layers;
+    L.F1 = c.ffn + (L.adapter ? c.adapter_dim : 0);
+    add_ln(h, p + ".ln1", &L.ln1, D);
+    add_ln(h, p + ".ln2", &L.ln2, D);
+    L.wqkv = h->alloc<bf16>((size_t)3 * D * D);
+    L.bqkv = h->alloc<float>((size_t)3 * D);
+    const char* qkvn[3] = {".q", ".k", ".v"};
+    for (int j = 0; j < 3; ++j) {
+      add_mat(h, p + qkvn[j] + ".weight", L.wqkv + (size_t)j * D * D, D, D, D);
+      Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.bqkv + (size_t)j * D;
+      h->slots[p + qkvn[j] + ".bias"] = s;
+    }
+    L.wo = h->alloc<bf16>((size_t)D * D);
+    add_mat(h, p + ".o.weight", L.wo, D, D, D);
+    add_vec(h, p + ".o.bias", &L.bo, D);
+    L.w1 = h->alloc<bf16>((size_t)L.F1 * D);
+    L.b1 = h->alloc<float>(L.F1);
+    L.w2 = h->alloc<bf16>((size_t)D * L.F1);
+    L.b2_raw = h->alloc<float>(D);
+    L.bu_raw = h->alloc<float>(D);
+    L.b2 = h->alloc<float>(D);
+    add_mat(h, p + ".ff1.weight", L.w1, c.ffn, D, D);
+    { Slot s; s.kind = SLOT_VEC; s.numel = c.ffn; s.fdst = L.b1; h->slots[p + ".ff1.bias"] = s; }
+    add_mat(h, p + ".ff2.weight", L.w2, D, c.ffn, L.F1);
+    { Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.b2_raw; h->slots[p + ".ff2.bias"] = s; }
+    if (L.adapter) {
+      // y + s*(Wu relu(Wd u + bd) + bu)  ==  extra FFN hidden units with ReLU and weights s*Wu
+      add_mat(h, p + ".ad_down.weight", L.w1 + (size_t)c.ffn * D, c.adapter_dim, D, D);
+      { Slot s; s.kind = SLOT_VEC; s.numel = c.adapter_dim; s.fdst = L.b1 + c.ffn;
+        h->slots[p + ".ad_down.bias"] = s; }
+      add_mat(h, p + ".ad_up.weight", L.w2 + c.ffn, D, c.adapter_dim, L.F1, c.adapter_scale);
+      { Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.bu_raw; h->slots[p + ".ad_up.bias"] = s; }
+    }
+  }
+
+  // head
+  if (c.head_layers > 0) {
+    HeadW& H = h->head;
+    add_ln(h, "head.ln1", &H.ln1, D);
+    add_ln(h, "head.ln2", &H.ln2, D);
+    H.win = h->alloc<bf16>((size_t)3 * D * D);
+    add_mat(h, "head.in_proj.weight", H.win, 3 * D, D, D);
+    add_vec(h, "head.in_proj.bias", &H.bin, 3 * D);
+    H.wo = h->alloc<bf16>((size_t)D * D);
+    add_mat(h, "head.o.weight", H.wo, D, D, D);
+    add_vec(h, "head.o.bias", &H.bo, D);
+    H.w1 = h->alloc<bf16>((size_t)c.head_ffn * D);
+    add_mat(h, "head.ff1.weight", H.w1, c.head_ffn, D, D);
+    add_vec(h, "head.ff1.bias", &H.b1, c.head_ffn);
+    H.w2 = h->alloc<bf16>((size_t)D * c.head_ffn);
+    add_mat(h, "head.ff2.weight", H.w2, D, c.head_ffn, c.head_ffn);
+    add_vec(h, "head.ff2.bias", &H.b2, D);
+  }
+  add_ln(h, "head.ln_f", &h->head.lnf, D);
+  add_vec(h, "head.out.weight", &h->head.wout, D);
+  add_vec(h, "head.out.bias", &h->head.bout, 1);
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves the workspace; with base == nullptr only computes the size.
+Workspace carve(const w2vseg_handle* h, uint8_t* base, int B, int R) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    off = align_up(off, 1024);
+    uint8_t* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  const size_t M = (size_t)B * R;
+  const int D = h->D, CD = h->cfg.conv_dim;
+  w.stats = reinterpret_cast<float2*>(take(sizeof(float2) * B));
+  w.enc_len = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * B));
+  for (int l = 0; l < 7; ++l) {
+    const size_t rows = M << (6 - l);
+    w.conv[l] = reinterpret_cast<bf16*>(take((rows + 4) * CD * sizeof(bf16)));
+  }
+  w.feat = reinterpret_cast<bf16*>(take(M * CD * sizeof(bf16)));
+  w.h = reinterpret_cast<float*>(take(M * D * sizeof(float)));
+  w.zpad = reinterpret_cast<bf16*>(take(((size_t)B * (R + 2 * kHalo) + 2 * kHalo) * D * sizeof(bf16)));
+  w.xn = reinterpret_cast<bf16*>(take(M * D * sizeof(bf16)));
+  w.qkv = reinterpret_cast<bf16*>(take(M * 3 * D * sizeof(bf16)));
+  w.ctx = reinterpret_cast<bf16*>(take(M * D * sizeof(bf16)));
+  w.mid = reinterpret_cast<bf16*>(take(M * (size_t)h->F1max * sizeof(bf16)));
+  w.bytes = align_up(off, 1024);
+  return w;
+}
+
+GemmProblem linear(const bf16* A, int64_t M, int K, const bf16* W, int N, const float* bias) {
+  GemmProblem g = {};
+  g.A = A; g.a_rows = M; g.a_row_stride = K; g.a_cols = K;
+  g.W = W; g.N = N; g.K = K;
+  g.num_groups = 1; g.rows_per_group = (int)M; g.a_group_rows = 0; g.o_group_rows = 0;
+  g.a_mode = 0;
+  g.bias = bias;
+  g.act_split = N; g.act_lo = ACT_NONE; g.act_hi = ACT_NONE;
+  g.resid = nullptr; g.ld_resid = 0;
+  g.out = nullptr; g.ld_out = N; g.out_f32 = 0;
+  g.mask_len = nullptr; g.mask_period = 1;
+  return g;
+}
+
+int check_ready(const w2vseg_handle* h) {
+  if (h == nullptr) { set_error("null handle"); return W2VSEG_ERR_ARG; }
+  if (!h->finalized) {
+    set_error("weights are not finalised: call w2vseg_set_weight for every tensor, then "
+              "w2vseg_finalize_weights");
+    return W2VSEG_ERR_STATE;
+  }
+  return 0;
+}
+
+// ---- encoder: audio -> h (fp32 [B*R, D]) -------------------------------------------------------
+int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_t audio_stride,
+                const int32_t* sample_len, const int32_t* norm_len, int B, int R, cudaStream_t st) {
+  const w2vseg_config& c = h->cfg;
+  const int D = h->D, CD = c.conv_dim;
+  const int64_t M = (int64_t)B * R;
+
+  W2V_TRY(window_stats_launch(audio, audio_stride, sample_len, norm_len, B, w.stats, w.enc_len, st));
+
+  // conv feature extractor (HF:382-419). Layer l activations: channels-last bf16 [B*R*2^(6-l), 512].
+  const int R0 = R << 6;
+  W2V_TRY(conv0_ln_gelu_launch(audio, audio_stride, sample_len, w.stats, h->conv0_wt, h->conv_b[0],
+                               h->conv_ln[0].g, h->conv_ln[0].b, c.ln_eps, w.conv[0], B, R0, st));
+  for (int l = 1; l < 7; ++l) {
+    const int64_t rows_in = M << (7 - l), rows_out = M << (6 - l);
+    // the last output row's im2col view runs (k-2) rows past the input: keep that slack finite
+    W2V_CHECK_CUDA(cudaMemsetAsync(w.conv[l - 1] + rows_in * CD, 0, (size_t)4 * CD * sizeof(bf16), st));
+    GemmProblem g = linear(w.conv[l - 1], rows_out, kConvK[l] * CD, h->conv_w[l], CD, h->conv_b[l]);
+    g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
+    g.out = w.conv[l]; g.ld_out = CD;
+    W2V_TRY(gemm_tc_launch(g, 256, st));
+    W2V_TRY(layernorm_launch(w.conv[l], false, rows_out, CD, h->conv_ln[l].g, h->conv_ln[l].b,
+                             c.ln_eps, /*gelu*/ 1, w.conv[l], st));
+  }
+
+  // feature projection (HF:429-434) with the frame mask fused (HF:753-756)
+  W2V_TRY(layernorm_launch(w.conv[6], false, M, CD, h->fp_ln.g, h->fp_ln.b, c.ln_eps, 0, w.feat, st));
+  {
+    GemmProblem g = linear(w.feat, M, CD, h->fp_w, D, h->fp_b);
+    g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+    g.mask_len = w.enc_len; g.mask_period = R;
+    W2V_TRY(gemm_tc_launch(g, 256, st));
+  }
+
+  // positional conv embedding (HF:360-368) + residual (HF:764-765)
+  W2V_CHECK_CUDA(cudaMemsetAsync(w.zpad, 0, ((size_t)B * (R + 2 * kHalo) + 2 * kHalo) * D * sizeof(bf16), st));
+  W2V_TRY(cast_to_padded_launch(w.h, B, R, D, kHalo, w.zpad, st));
+  {
+    const int gc = D / c.pos_groups;
+    W2V_REQUIRE(gc == 64, "positional conv: %d channels per group unsupported (64 only)", gc);
+    GemmProblem g = {};
+    g.A = w.zpad; g.a_rows = (int64_t)B * (R + 2 * kHalo) + 2 * kHalo; g.a_row_stride = D; g.a_cols = D;
+    g.W = h->pos_w; g.N = D; g.K = gc * c.pos_kernel;
+    g.num_groups = B; g.rows_per_group = R; g.a_group_rows = R + 2 * kHalo; g.o_group_rows = R;
+    g.a_mode = 1;
+    g.bias = h->pos_b; g.act_split = D; g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
+    g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+    g.mask_len = nullptr; g.mask_period = 1;
+    W2V_TRY(gemm_tc_launch(g, 64, st));
+  }
+
+  // transformer layers (pre-LN "stable layer norm" variant, HF:632-655; adapter lib/models.py:404-428)
+  for (int i = 0; i < c.n_layers; ++i) {
+    const EncLayerW& L = h->enc[i];
+    W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln1.g, L.ln1.b, c.ln_eps, 0, w.xn, st));
+    {
+      GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
+      g.out = w.qkv; g.ld_out = 3 * D;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    W2V_TRY(attention_launch(w.qkv, B, R, c.heads, h->DH, w.enc_len, 1.0f / sqrtf((float)h->DH),
+                             w.ctx, st));
+    {
+      GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
+      g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln2.g, L.ln2.b, c.ln_eps, 0, w.xn, st));
+    {
+      GemmProblem g = linear(w.xn, M, D, L.w1, L.F1, L.b1);
+      g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
+      g.out = w.mid; g.ld_out = L.F1;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    {
+      GemmProblem g = linear(w.mid, M, L.F1, L.w2, D, L.b2);
+      g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+  }
+  return 0;
+}
+
+// ---- head: y (fp32 [B*R, D], updated in place) -> logits / probs --------------------------------
+int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const int32_t* out_len,
+             float* logits, float* probs, cudaStream_t st) {
+  const w2vseg_config& c = h->cfg;
+  const int D = h->D;
+  const int64_t M = (int64_t)B * R;
+  if (c.head_layers > 0) {
+    const HeadW& H = h->head;
+    const int hd = D / c.head_heads;
+    W2V_TRY(layernorm_launch(y, true, M, D, H.ln1.g, H.ln1.b, c.ln_eps, 0, w.xn, st));
+    {
+      GemmProblem g = linear(w.xn, M, D, H.win, 3 * D, H.bin);
+      g.out = w.qkv; g.ld_out = 3 * D;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    W2V_TRY(attention_launch(w.qkv, B, R, c.head_heads, hd, out_len, 1.0f / sqrtf((float)hd), w.ctx, st));
+    {
+      GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
+      g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    W2V_TRY(layernorm_launch(y, true, M, D, H.ln2.g, H.ln2.b, c.ln_eps, 0, w.xn, st));
+    {
+      GemmProblem g = linear(w.xn, M, D, H.w1, c.head_ffn, H.b1);
+      g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
+      g.out = w.mid; g.ld_out = c.head_ffn;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+    {
+      GemmProblem g = linear(w.mid, M, c.head_ffn, H.w2, D, H.b2);
+      g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      W2V_TRY(gemm_tc_launch(g, 256, st));
+    }
+  }
+  W2V_TRY(head_final_launch(y, B, R, D, h->head.lnf.g, h->head.lnf.b, c.ln_eps, h->head.wout,
+                            h->head.bout, out_len, logits, probs, st));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t w2vseg_create(const w2vseg_config* cfg, w2vseg_handle** out) {
+  W2V_REQUIRE(cfg != nullptr && out != nullptr, "create: null argument");
+  W2V_REQUIRE(cfg->hidden == 1024 && cfg->conv_dim == 512,
+              "create: hidden=%d conv_dim=%d unsupported (XLS-R-300m geometry 1024/512 only)",
+              cfg->hidden, cfg->conv_dim);
+  W2V_REQUIRE(cfg->heads > 0 && cfg->hidden / cfg->heads == 64, "create: encoder head_dim must be 64");
+  W2V_REQUIRE(cfg->n_layers >= 0 && cfg->n_adapter_layers >= 0 && cfg->n_adapter_layers <= cfg->n_layers,
+              "create: bad layer counts (%d layers, %d adapters)", cfg->n_layers, cfg->n_adapter_layers);
+  W2V_REQUIRE(cfg->ffn % 256 == 0 && cfg->adapter_dim % 256 == 0 && cfg->head_ffn % 256 == 0,
+              "create: ffn/adapter/head_ffn sizes must be multiples of 256");
+  W2V_REQUIRE(cfg->pos_kernel == 128 && cfg->pos_groups == 16, "create: positional conv must be k=128, g=16");
+  W2V_REQUIRE(cfg->head_layers == 0 || cfg->head_layers == 1, "create: head_layers must be 0 or 1");
+  if (cfg->head_layers == 1) {
+    const int hd = cfg->hidden / (cfg->head_heads > 0 ? cfg->head_heads : 1);
+    W2V_REQUIRE(cfg->head_heads > 0 && (hd == 64 || hd == 128), "create: head head_dim must be 64 or 128");
+  }
+  W2V_TRY(w2vseg_device_ok());
+
+  w2vseg_handle* h = new w2vseg_handle();
+  h->cfg = *cfg;
+  h->D = cfg->hidden;
+  h->DH = cfg->hidden / cfg->heads;
+  h->F1max = cfg->ffn + (cfg->n_adapter_layers > 0 ? cfg->adapter_dim : 0);
+  if (cfg->head_layers > 0 && cfg->head_ffn > h->F1max) h->F1max = cfg->head_ffn;
+  build_layout(h);  // sizing pass
+  h->arena_bytes = h->arena_used + 4096;
+  if (cudaMalloc(&h->arena, h->arena_bytes) != cudaSuccess) {
+    set_error("create: cudaMalloc of %zu weight bytes failed", h->arena_bytes);
+    delete h;
+    return W2VSEG_ERR_CUDA;
+  }
+  build_layout(h);
+  *out = h;
+  return 0;
+}
+
+void w2vseg_destroy(w2vseg_handle* h) {
+  if (h == nullptr) return;
+  if (h->arena != nullptr) cudaFree(h->arena);
+  delete h;
+}
+
+int32_t w2vseg_set_weight(w2vseg_handle* h, const char* name, const float* src, int64_t numel,
+                          void* stream) {
+  W2V_REQUIRE(h != nullptr && name != nullptr && src != nullptr, "set_weight: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = h->slots.find(name);
+  W2V_REQUIRE(it != h->slots.end(), "set_weight: unknown tensor name '%s'", name);
+  const Slot& s = it->second;
+  W2V_REQUIRE(numel == s.numel, "set_weight: '%s' has %lld elements, expected %lld", name,
+              (long long)numel, (long long)s.numel);
+  switch (s.kind) {
+    case SLOT_VEC:
+      W2V_TRY(axpby_launch(src, s.scale, nullptr, 0.f, s.fdst, (int)s.numel, st));
+      break;
+    case SLOT_RAW:
+      W2V_CHECK_CUDA(cudaMemcpyAsync(s.fdst, src, s.numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    case SLOT_MAT:
+      W2V_TRY(pack_matrix_launch(src, s.rows, s.cols, s.scale, s.bdst, s.ld, st));
+      break;
+    case SLOT_CONV:
+      W2V_TRY(pack_conv_launch(src, s.O, s.I, s.J, nullptr, s.bdst, st));
+      break;
+    case SLOT_CONV0:
+      W2V_TRY(transpose_f32_launch(src, s.O, s.J, s.fdst, st));
+      break;
+  }
+  h->was_set[name] = true;
+  h->finalized = false;
+  return 0;
+}
+
+int32_t w2vseg_finalize_weights(w2vseg_handle* h, void* stream) {
+  W2V_REQUIRE(h != nullptr, "finalize: null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool has_gv = h->was_set.count("pos.weight_g") && h->was_set.count("pos.weight_v");
+  const bool has_w = h->was_set.count("pos.weight") > 0;
+  for (const auto& kv : h->slots) {
+    if (kv.second.alt_group != 0) continue;
+    if (!h->was_set.count(kv.first)) {
+      set_error("finalize: tensor '%s' was never set", kv.first.c_str());
+      return W2VSEG_ERR_STATE;
+    }
+  }
+  if (!has_gv && !has_w) {
+    set_error("finalize: positional conv needs pos.weight_g + pos.weight_v (weight-norm) or pos.weight");
+    return W2VSEG_ERR_STATE;
+  }
+  const w2vseg_config& c = h->cfg;
+  if (has_gv) {
+    // weight_norm(dim=2): W[o,i,j] = g[j] * v[o,i,j] / ||v[:,:,j]||  (HF:343-355)
+    const int gc = h->D / c.pos_groups;
+    W2V_TRY(weightnorm_scale_launch(h->pos_v, h->pos_g, h->D * gc, c.pos_kernel, h->pos_scale, st));
+    W2V_TRY(pack_conv_launch(h->pos_v, h->D, gc, c.pos_kernel, h->pos_scale, h->pos_w, st));
+  }
+  for (auto& L : h->enc) {
+    if (L.adapter) W2V_TRY(axpby_launch(L.b2_raw, 1.f, L.bu_raw, c.adapter_scale, L.b2, h->D, st));
+    else W2V_TRY(axpby_launch(L.b2_raw, 1.f, nullptr, 0.f, L.b2, h->D, st));
+  }
+  h->finalized = true;
+  return 0;
+}
+
+size_t w2vseg_workspace_bytes(const w2vseg_handle* h, int32_t B, int64_t l_max) {
+  if (h == nullptr || B <= 0 || l_max <= 0) return 0;
+  const int R = w2vseg_frame_stride(l_max);
+  return carve(h, nullptr, B, R).bytes + 1024;
+}
+
+static int check_ws(const w2vseg_handle* h, void* workspace, size_t workspace_bytes, int B, int R,
+                    Workspace* w) {
+  W2V_REQUIRE(workspace != nullptr, "null workspace");
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  *w = carve(h, base, B, R);
+  const size_t need = w->bytes + (size_t)(base - reinterpret_cast<uint8_t*>(workspace));
+  W2V_REQUIRE(workspace_bytes >= need, "workspace too small: %zu bytes given, %zu needed (B=%d, R=%d)",
+              workspace_bytes, need, B, R);
+  return 0;
+}
+
+int32_t w2vseg_encode(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                      const int32_t* sample_len, const int32_t* norm_len, int32_t B, int64_t l_max,
+                      float* hidden_out, int32_t* enc_len_out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(audio && sample_len && norm_len && hidden_out, "encode: null argument");
+  W2V_REQUIRE(B > 0 && l_max >= 400 && audio_stride >= l_max, "encode: bad shape (B=%d, l_max=%lld, stride=%lld)",
+              B, (long long)l_max, (long long)audio_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = w2vseg_frame_stride(l_max);
+  Workspace w;
+  W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_CHECK_CUDA(cudaMemcpyAsync(hidden_out, w.h, (size_t)B * R * h->D * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+  if (enc_len_out != nullptr)
+    W2V_CHECK_CUDA(cudaMemcpyAsync(enc_len_out, w.enc_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int32_t w2vseg_head(w2vseg_handle* h, const float* hidden, int64_t batch_stride, int32_t T,
+                    const int32_t* out_len, int32_t B, float* logits_out, float* probs_out,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(hidden && out_len, "head: null argument");
+  W2V_REQUIRE(B > 0 && T > 0 && batch_stride >= (int64_t)T * h->D && batch_stride % 4 == 0,
+              "head: bad shape (B=%d, T=%d, batch_stride=%lld)", B, T, (long long)batch_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the workspace was sized for R >= T rows per window; use T as the row stride here
+  Workspace w;
+  W2V_TRY(check_ws(h, workspace, workspace_bytes, B, T, &w));
+  W2V_TRY(gather_rows_launch(hidden, batch_stride, B, T, h->D, w.h, st));
+  W2V_TRY(run_head(h, w, w.h, B, T, out_len, logits_out, probs_out, st));
+  return 0;
+}
+
+int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                           const int32_t* sample_len, const int32_t* norm_len,
+                           const int32_t* out_len, int32_t B, int64_t l_max, float* logits_out,
+                           float* probs_out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(audio && sample_len && norm_len && out_len, "sfc_forward: null argument");
+  W2V_REQUIRE(B > 0 && l_max >= 400 && audio_stride >= l_max,
+              "sfc_forward: bad shape (B=%d, l_max=%lld, stride=%lld)", B, (long long)l_max,
+              (long long)audio_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = w2vseg_frame_stride(l_max);
+  Workspace w;
+  W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_TRY(run_head(h, w, w.h, B, R, out_len, logits_out, probs_out, st));
+  return 0;
+}
+
+// ---- talk-level reductions -------------------------------------------------------------------
+int32_t w2vseg_scatter_rows(const float* rows, int64_t row_stride, const int32_t* start,
+                            const int32_t* count, int32_t n_rows, double* talk, int64_t n_frames,
+                            void* stream) {
+  W2V_REQUIRE(talk != nullptr && n_frames >= 0 && n_rows >= 0, "scatter_rows: bad argument");
+  W2V_REQUIRE(n_rows == 0 || (rows && start && count), "scatter_rows: null argument");
+  return scatter_rows_launch(rows, row_stride, start, count, n_rows, talk, n_frames, (cudaStream_t)stream);
+}
+int32_t w2vseg_nanfill(double* talk, int64_t n_frames, const int32_t* idx, int32_t n_idx, void* stream) {
+  W2V_REQUIRE(talk != nullptr && (n_idx == 0 || idx != nullptr), "nanfill: null argument");
+  return nanfill_launch(talk, n_frames, idx, n_idx, (cudaStream_t)stream);
+}
+int32_t w2vseg_overlap_average(const double* tilings, int32_t n_tilings, int64_t n_frames,
+                               double* out, void* stream) {
+  W2V_REQUIRE(tilings && out, "overlap_average: null argument");
+  return overlap_average_launch(tilings, n_tilings, n_frames, out, (cudaStream_t)stream);
+}
+int32_t w2vseg_moving_average(const double* arr, int64_t n, int32_t window, double* out, void* stream) {
+  W2V_REQUIRE(arr && out && arr != out, "moving_average: null or aliased argument");
+  return moving_average_launch(arr, n, window, out, (cudaStream_t)stream);
+}
+
+// ---- single kernels -----------------------------------------------------------------------------
+int32_t w2vseg_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias,
+                    int32_t act, const float* resid, void* out, int32_t out_f32, int32_t block_n,
+                    void* stream) {
+  W2V_REQUIRE(A && W && out && M > 0, "gemm: bad argument");
+  W2V_TRY(w2vseg_device_ok());
+  GemmProblem g = linear((const bf16*)A, M, K, (const bf16*)W, N, bias);
+  g.act_lo = act; g.act_hi = act;
+  g.resid = resid; g.ld_resid = N; g.out = out; g.ld_out = N; g.out_f32 = out_f32;
+  return gemm_tc_launch(g, block_n, (cudaStream_t)stream);
+}
+
+int32_t w2vseg_conv_gemm(const void* x, int64_t rows_out, int32_t C, int32_t kw, int32_t stride,
+                         const void* W, int32_t N, const float* bias, void* out, void* stream) {
+  W2V_REQUIRE(x && W && out && rows_out > 0, "conv_gemm: bad argument");
+  W2V_TRY(w2vseg_device_ok());
+  GemmProblem g = linear((const bf16*)x, rows_out, kw * C, (const bf16*)W, N, bias);
+  g.a_row_stride = (int64_t)stride * C;
+  g.out = out; g.ld_out = N;
+  return gemm_tc_launch(g, N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64), (cudaStream_t)stream);
+}
+
+int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C, const float* gamma,
+                         const float* beta, float eps, int32_t act, void* out, void* stream) {
+  W2V_REQUIRE(in && gamma && beta && out, "layernorm: null argument");
+  return layernorm_launch(in, in_f32 != 0, rows, C, gamma, beta, eps, act, (bf16*)out, (cudaStream_t)stream);
+}
+
+int32_t w2vseg_attention(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                         const int32_t* kv_len, float scale, void* ctx, void* stream) {
+  W2V_REQUIRE(qkv && kv_len && ctx, "attention: null argument");
+  return attention_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

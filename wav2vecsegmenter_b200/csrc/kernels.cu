@@ -1,0 +1,611 @@
+// Memory-bound / CUDA-core kernels of the SFC path: coalesced, 128-bit vectorised, warp-shuffle
+// reductions, one warp per row wherever a row is a LayerNorm group.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace w2v {
+
+namespace {
+
+// =============================================================================================
+// window statistics  (lib/datautils.py:122-125: mean / unbiased std over the zero-padded row)
+// =============================================================================================
+__device__ __forceinline__ int conv_frames(long long n) {
+  const int k[7] = {10, 3, 3, 3, 3, 2, 2};
+  const int s[7] = {5, 2, 2, 2, 2, 2, 2};
+#pragma unroll
+  for (int l = 0; l < 7; ++l) {
+    if (n < k[l]) return 0;
+    n = (n - k[l]) / s[l] + 1;
+  }
+  return (int)n;
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  double t = (lane < nw) ? sh[lane] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;  // every thread holds the block total
+}
+
+__global__ void __launch_bounds__(1024)
+window_stats_kernel(const float* __restrict__ audio, long long audio_stride,
+                    const int* __restrict__ sample_len, const int* __restrict__ norm_len,
+                    float2* __restrict__ stats, int* __restrict__ enc_len) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  const int len = sample_len[b];
+  const int nl = norm_len[b];
+  if (threadIdx.x == 0 && enc_len != nullptr) enc_len[b] = conv_frames(len);
+  if (nl <= 0) {
+    if (threadIdx.x == 0) stats[b] = make_float2(0.f, 1.f);
+    return;
+  }
+  const float* x = audio + (long long)b * audio_stride;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) s += (double)x[i];
+  const double mean = block_sum_f64(s, sh) / (double)nl;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const double d = (double)x[i] - mean;
+    q += d * d;
+  }
+  double ss = block_sum_f64(q, sh);
+  ss += (double)(nl - len) * mean * mean;  // the zero padding is part of the reference's row
+  if (threadIdx.x == 0) {
+    const double var = ss / (double)(nl - 1);
+    stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var)));
+  }
+}
+
+// =============================================================================================
+// conv layer 0 + LayerNorm(512) + GELU   (HF:281-299, Wav2Vec2LayerNormConvLayer with Cin = 1)
+// one warp per output frame; lane owns channels q*128 + lane*4 + e  (q, e in 0..3)
+// =============================================================================================
+constexpr int C0_ROWS = 128;   // frames per block
+constexpr int C0_THREADS = 256;
+
+__global__ void __launch_bounds__(C0_THREADS)
+conv0_ln_gelu_kernel(const float* __restrict__ audio, long long audio_stride,
+                     const int* __restrict__ sample_len, const float2* __restrict__ stats,
+                     const float* __restrict__ w_t, const float* __restrict__ bias,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     __nv_bfloat16* __restrict__ out, int R0) {
+  __shared__ float4 w_s[10 * 128];
+  __shared__ float x_s[C0_ROWS * 5 + 8];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0_ROWS;
+  const int len = sample_len[b];
+  const float2 st = stats[b];
+  const float* x = audio + (long long)b * audio_stride;
+
+  for (int i = threadIdx.x; i < 10 * 128; i += C0_THREADS)
+    w_s[i] = reinterpret_cast<const float4*>(w_t)[i];
+  for (int i = threadIdx.x; i < C0_ROWS * 5 + 5; i += C0_THREADS) {
+    const long long sidx = (long long)t0 * 5 + i;
+    x_s[i] = (sidx < len) ? (x[sidx] - st.x) * st.y : 0.f;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float bi[16], ga[16], be[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v0 = reinterpret_cast<const float4*>(bias)[q * 32 + lane];
+    const float4 v1 = reinterpret_cast<const float4*>(gamma)[q * 32 + lane];
+    const float4 v2 = reinterpret_cast<const float4*>(beta)[q * 32 + lane];
+    bi[4 * q] = v0.x; bi[4 * q + 1] = v0.y; bi[4 * q + 2] = v0.z; bi[4 * q + 3] = v0.w;
+    ga[4 * q] = v1.x; ga[4 * q + 1] = v1.y; ga[4 * q + 2] = v1.z; ga[4 * q + 3] = v1.w;
+    be[4 * q] = v2.x; be[4 * q + 1] = v2.y; be[4 * q + 2] = v2.z; be[4 * q + 3] = v2.w;
+  }
+
+  for (int tl = warp; tl < C0_ROWS; tl += C0_THREADS / 32) {
+    const int t = t0 + tl;
+    if (t >= R0) break;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = bi[c];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float xv = x_s[tl * 5 + j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = w_s[j * 128 + q * 32 + lane];
+        acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s += acc[c];
+    const float mean = warp_sum(s) * (1.f / 512.f);
+    float qv = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float d = acc[c] - mean;
+      qv = fmaf(d, d, qv);
+    }
+    const float rstd = rsqrtf(warp_sum(qv) * (1.f / 512.f) + eps);
+    __nv_bfloat16* o = out + ((long long)b * R0 + t) * 512;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float y[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        y[e] = gelu_erf(fmaf((acc[4 * q + e] - mean) * rstd, ga[4 * q + e], be[4 * q + e]));
+      uint2 u;
+      u.x = pack_bf16x2(y[0], y[1]);
+      u.y = pack_bf16x2(y[2], y[3]);
+      reinterpret_cast<uint2*>(o)[q * 32 + lane] = u;
+    }
+  }
+}
+
+// =============================================================================================
+// LayerNorm (+ optional GELU): one warp per row, two-pass statistics in registers
+// =============================================================================================
+template <int C, bool IN_F32, int ACT>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* in_, long long rows, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* out) {
+  constexpr int PER_LANE = C / 32;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[PER_LANE];
+  if constexpr (IN_F32) {
+    const float4* p = reinterpret_cast<const float4*>(in_) + row * (C / 4);
+#pragma unroll
+    for (int i = 0; i < PER_LANE / 4; ++i) {
+      const float4 f = p[i * 32 + lane];
+      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+  } else {
+    const uint4* p = reinterpret_cast<const uint4*>(in_) + row * (C / 8);
+#pragma unroll
+    for (int i = 0; i < PER_LANE / 8; ++i) {
+      const uint4 u = p[i * 32 + lane];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+        v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+
+  constexpr int VEC = IN_F32 ? 4 : 8;  // elements per lane per contiguous group
+#pragma unroll
+  for (int i = 0; i < PER_LANE / VEC; ++i) {
+    const int col = (i * 32 + lane) * VEC;
+    float y[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + col + k);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + col + k);
+      y[k + 0] = fmaf((v[VEC * i + k + 0] - mean) * rstd, g.x, bt.x);
+      y[k + 1] = fmaf((v[VEC * i + k + 1] - mean) * rstd, g.y, bt.y);
+      y[k + 2] = fmaf((v[VEC * i + k + 2] - mean) * rstd, g.z, bt.z);
+      y[k + 3] = fmaf((v[VEC * i + k + 3] - mean) * rstd, g.w, bt.w);
+    }
+    if constexpr (ACT == 1) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) y[k] = gelu_erf(y[k]);
+    }
+    __nv_bfloat16* o = out + row * C + col;
+    if constexpr (VEC == 4) {
+      uint2 u;
+      u.x = pack_bf16x2(y[0], y[1]);
+      u.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(o) = u;
+    } else {
+      uint4 u;
+      u.x = pack_bf16x2(y[0], y[1]);
+      u.y = pack_bf16x2(y[2], y[3]);
+      u.z = pack_bf16x2(y[4], y[5]);
+      u.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(o) = u;
+    }
+  }
+}
+
+// =============================================================================================
+// small data-movement kernels
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+cast_to_padded_kernel(const float* __restrict__ h, int R, int C, int halo,
+                      __nv_bfloat16* __restrict__ zpad, long long total_vec4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec4) return;
+  const int c4 = C / 4;
+  const long long row = i / c4;
+  const int col = (int)(i - row * c4) * 4;
+  const long long b = row / R;
+  const long long t = row - b * R;
+  const float4 f = reinterpret_cast<const float4*>(h)[i];
+  uint2 u;
+  u.x = pack_bf16x2(f.x, f.y);
+  u.y = pack_bf16x2(f.z, f.w);
+  *reinterpret_cast<uint2*>(zpad + (b * (R + 2 * halo) + halo + t) * C + col) = u;
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, long long batch_stride, int T, int C,
+                   float* __restrict__ dst, long long total_vec4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec4) return;
+  const long long per_b = (long long)T * C / 4;
+  const long long b = i / per_b;
+  const long long r = i - b * per_b;
+  reinterpret_cast<float4*>(dst)[i] =
+      *reinterpret_cast<const float4*>(src + b * batch_stride + r * 4);
+}
+
+// =============================================================================================
+// head: LayerNorm(C) -> dot(w) + b -> sigmoid -> mask      (one warp per frame, C = 1024)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+head_final_kernel(const float* __restrict__ y, long long rows, int R,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  const float* __restrict__ w_out, const float* __restrict__ b_out,
+                  const int* __restrict__ out_len, float* __restrict__ logits,
+                  float* __restrict__ probs) {
+  constexpr int C = 1024;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[32];
+  const float4* p = reinterpret_cast<const float4*>(y) + row * (C / 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 f = p[i * 32 + lane];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+    const float4 w = *reinterpret_cast<const float4*>(w_out + col);
+    dot = fmaf(fmaf((v[4 * i + 0] - mean) * rstd, g.x, bt.x), w.x, dot);
+    dot = fmaf(fmaf((v[4 * i + 1] - mean) * rstd, g.y, bt.y), w.y, dot);
+    dot = fmaf(fmaf((v[4 * i + 2] - mean) * rstd, g.z, bt.z), w.z, dot);
+    dot = fmaf(fmaf((v[4 * i + 3] - mean) * rstd, g.w, bt.w), w.w, dot);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    const long long b = row / R;
+    const int t = (int)(row - b * R);
+    const bool keep = t < out_len[b];
+    const float logit = dot + b_out[0];
+    if (logits != nullptr) logits[row] = keep ? logit : 0.f;
+    if (probs != nullptr) probs[row] = keep ? 1.f / (1.f + expf(-logit)) : 0.f;
+  }
+}
+
+// =============================================================================================
+// weight packing
+// =============================================================================================
+__global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int cols, float scale,
+                                   __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  dst[r * ld_dst + c] = __float2bfloat16_rn(src[i] * scale);
+}
+
+__global__ void pack_conv_kernel(const float* __restrict__ src, int O, int I, int J,
+                                 const float* __restrict__ tap_scale,
+                                 __nv_bfloat16* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over dst [O][J][I]
+  if (i >= (long long)O * I * J) return;
+  const int ci = (int)(i % I);
+  const int j = (int)((i / I) % J);
+  const long long o = i / ((long long)I * J);
+  float v = src[(o * I + ci) * J + j];
+  if (tap_scale != nullptr) v *= tap_scale[j];
+  dst[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int O, int J,
+                                     float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * J) return;
+  const int o = i / J, j = i - o * J;
+  dst[j * O + o] = src[i];
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b,
+                             float sb, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = a[i] * sa + (b != nullptr ? b[i] * sb : 0.f);
+}
+
+// one block per tap j: ||v[:, :, j]||_2 over OI entries (stride J), fp64 accumulation
+__global__ void __launch_bounds__(1024)
+weightnorm_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int OI, int J,
+                        float* __restrict__ scale) {
+  __shared__ double sh[32];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < OI; i += blockDim.x) {
+    const double x = (double)v[(long long)i * J + j];
+    s += x * x;
+  }
+  const double tot = block_sum_f64(s, sh);
+  if (threadIdx.x == 0) scale[j] = (float)((double)g[j] / sqrt(tot));
+}
+
+// =============================================================================================
+// talk-level reductions
+// =============================================================================================
+__global__ void fill_nan_kernel(double* __restrict__ talk, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) talk[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// one block per window row; coalesced fp32 reads, fp64 writes
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const float* __restrict__ rows, long long row_stride,
+                    const int* __restrict__ start, const int* __restrict__ count,
+                    double* __restrict__ talk, long long n_frames) {
+  const int w = blockIdx.x;
+  const int cnt = count[w];
+  const long long s0 = start[w];
+  if (cnt >= 0) {
+    const float* r = rows + (long long)w * row_stride;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const long long d = s0 + i;
+      if (d >= 0 && d < n_frames) talk[d] = (double)r[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < -cnt; i += blockDim.x) {
+      const long long d = s0 + i;
+      if (d >= 0 && d < n_frames) talk[d] = 0.0;
+    }
+  }
+}
+
+// Sequential by construction (a filled frame feeds the next fill, lib/evaluate.py:118-125);
+// the list is a handful of frames per talk. Summation order = numpy's for n < 8: left to right.
+__global__ void nanfill_kernel(double* __restrict__ talk, long long n, const int* __restrict__ idx,
+                               int n_idx) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int k = 0; k < n_idx; ++k) {
+    const long long j = idx[k];
+    if (j < 0 || j >= n) continue;
+    const long long a = j - 2 > 0 ? j - 2 : 0;
+    const long long b = j + 3 < n ? j + 3 : n;
+    double s = 0.0;
+    int cnt = 0;
+    for (long long i = a; i < b; ++i) {
+      const double x = talk[i];
+      if (x == x) { s += x; ++cnt; }
+    }
+    talk[j] = s / (double)cnt;  // 0/0 = NaN exactly like np.nanmean of an all-NaN slice
+  }
+}
+
+__global__ void __launch_bounds__(256)
+overlap_average_kernel(const double* __restrict__ tilings, int n_tilings, long long n,
+                       double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = tilings[i];
+  for (int k = 1; k < n_tilings; ++k) s += tilings[(long long)k * n + i];
+  out[i] = s / (double)n_tilings;
+}
+
+// Each output is an independent left-to-right fp64 sum of <= window inputs: bit-identical to the
+// reference's Python `sum(part)/len(part)`. A block stages its span (+ window-1 halo) in shared
+// memory so every input is read from HBM once.
+constexpr int MA_THREADS = 256;
+__global__ void __launch_bounds__(MA_THREADS)
+moving_average_kernel(const double* __restrict__ arr, long long n, int window,
+                      double* __restrict__ out) {
+  extern __shared__ double ma_s[];
+  const long long i0 = (long long)blockIdx.x * MA_THREADS;
+  const long long lo = i0 - (window - 1);
+  const int span = MA_THREADS + window - 1;
+  for (int k = threadIdx.x; k < span; k += MA_THREADS) {
+    const long long g = lo + k;
+    ma_s[k] = (g >= 0 && g < n) ? arr[g] : 0.0;
+  }
+  __syncthreads();
+  const long long i = i0 + threadIdx.x;
+  if (i >= n) return;
+  const int cnt = (int)(i + 1 < window ? i + 1 : window);
+  const int first = threadIdx.x + (window - 1) - (cnt - 1);
+  double s = 0.0;
+  for (int k = 0; k < cnt; ++k) s += ma_s[first + k];
+  out[i] = s / (double)cnt;
+}
+
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                        const int32_t* norm_len, int B, float2* stats, int32_t* enc_len,
+                        cudaStream_t s) {
+  if (B <= 0) return 0;
+  window_stats_kernel<<<B, 1024, 0, s>>>(audio, audio_stride, sample_len, norm_len, stats, enc_len);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                         const float2* stats, const float* w_t, const float* bias,
+                         const float* gamma, const float* beta, float eps, __nv_bfloat16* out,
+                         int B, int R0, cudaStream_t s) {
+  if (B <= 0 || R0 <= 0) return 0;
+  dim3 grid((R0 + C0_ROWS - 1) / C0_ROWS, B);
+  conv0_ln_gelu_kernel<<<grid, C0_THREADS, 0, s>>>(audio, audio_stride, sample_len, stats, w_t,
+                                                   bias, gamma, beta, eps, out, R0);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const float* gamma,
+                     const float* beta, float eps, int act, __nv_bfloat16* out, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  const unsigned grid = blocks_for(rows, 8);
+#define W2V_LN(Cv, F32, ACTv)                                                                  \
+  layernorm_kernel<Cv, F32, ACTv><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, out)
+  if (C == 512 && !in_f32 && act == 0) W2V_LN(512, false, 0);
+  else if (C == 512 && !in_f32 && act == 1) W2V_LN(512, false, 1);
+  else if (C == 512 && in_f32 && act == 0) W2V_LN(512, true, 0);
+  else if (C == 1024 && in_f32 && act == 0) W2V_LN(1024, true, 0);
+  else if (C == 1024 && !in_f32 && act == 0) W2V_LN(1024, false, 0);
+  else {
+    set_error("layernorm: unsupported (C=%d, in_f32=%d, act=%d)", C, (int)in_f32, act);
+    return W2VSEG_ERR_ARG;
+  }
+#undef W2V_LN
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int cast_to_padded_launch(const float* h, int B, int R, int C, int halo, __nv_bfloat16* zpad,
+                          cudaStream_t s) {
+  const long long total = (long long)B * R * C / 4;
+  if (total <= 0) return 0;
+  cast_to_padded_kernel<<<blocks_for(total, 256), 256, 0, s>>>(h, R, C, halo, zpad, total);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int gather_rows_launch(const float* src, int64_t batch_stride, int B, int T, int C, float* dst,
+                       cudaStream_t s) {
+  const long long total = (long long)B * T * C / 4;
+  if (total <= 0) return 0;
+  gather_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, batch_stride, T, C, dst, total);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int head_final_launch(const float* y, int B, int R, int C, const float* gamma, const float* beta,
+                      float eps, const float* w_out, const float* b_out, const int32_t* out_len,
+                      float* logits, float* probs, cudaStream_t s) {
+  W2V_REQUIRE(C == 1024, "head_final: hidden size %d unsupported (1024 only)", C);
+  const long long rows = (long long)B * R;
+  if (rows <= 0) return 0;
+  head_final_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(y, rows, R, gamma, beta, eps, w_out, b_out,
+                                                        out_len, logits, probs);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int pack_matrix_launch(const float* src, int rows, int cols, float scale, __nv_bfloat16* dst,
+                       int64_t ld_dst, cudaStream_t s) {
+  const long long n = (long long)rows * cols;
+  pack_matrix_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, rows, cols, scale, dst, ld_dst);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_scale,
+                     __nv_bfloat16* dst, cudaStream_t s) {
+  const long long n = (long long)O * I * J;
+  pack_conv_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, O, I, J, tap_scale, dst);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int transpose_f32_launch(const float* src, int O, int J, float* dst, cudaStream_t s) {
+  transpose_f32_kernel<<<blocks_for((long long)O * J, 256), 256, 0, s>>>(src, O, J, dst);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int axpby_launch(const float* a, float sa, const float* b, float sb, float* dst, int n,
+                 cudaStream_t s) {
+  axpby_kernel<<<blocks_for(n, 256), 256, 0, s>>>(a, sa, b, sb, dst, n);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int weightnorm_scale_launch(const float* v, const float* g, int OI, int J, float* scale,
+                            cudaStream_t s) {
+  weightnorm_scale_kernel<<<J, 1024, 0, s>>>(v, g, OI, J, scale);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int scatter_rows_launch(const float* rows, int64_t row_stride, const int32_t* start,
+                        const int32_t* count, int n_rows, double* talk, int64_t n_frames,
+                        cudaStream_t s) {
+  if (n_frames > 0) {
+    fill_nan_kernel<<<blocks_for(n_frames, 256), 256, 0, s>>>(talk, n_frames);
+    W2V_CHECK_LAUNCH();
+  }
+  if (n_rows > 0) {
+    scatter_rows_kernel<<<n_rows, 256, 0, s>>>(rows, row_stride, start, count, talk, n_frames);
+    W2V_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int nanfill_launch(double* talk, int64_t n_frames, const int32_t* idx, int n_idx, cudaStream_t s) {
+  if (n_idx <= 0) return 0;
+  nanfill_kernel<<<1, 32, 0, s>>>(talk, n_frames, idx, n_idx);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int overlap_average_launch(const double* tilings, int n_tilings, int64_t n_frames, double* out,
+                           cudaStream_t s) {
+  W2V_REQUIRE(n_tilings >= 1, "overlap_average: n_tilings must be >= 1");
+  if (n_frames <= 0) return 0;
+  overlap_average_kernel<<<blocks_for(n_frames, 256), 256, 0, s>>>(tilings, n_tilings, n_frames,
+                                                                   out);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int moving_average_launch(const double* arr, int64_t n, int window, double* out, cudaStream_t s) {
+  W2V_REQUIRE(window >= 1, "moving_average: window must be >= 1 (the reference divides by zero)");
+  W2V_REQUIRE(window <= 4096, "moving_average: window %d too large (max 4096 frames)", window);
+  if (n <= 0) return 0;
+  const size_t smem = (size_t)(MA_THREADS + window - 1) * sizeof(double);
+  moving_average_kernel<<<blocks_for(n, MA_THREADS), MA_THREADS, smem, s>>>(arr, n, window, out);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace w2v

@@ -1,0 +1,70 @@
+// Launchers for the memory-bound / CUDA-core kernels of the SFC path (kernels.cu) and the fused
+// attention kernel (attention.cu). All take device pointers and a stream; all return 0 / W2VSEG_ERR_*.
+#pragma once
+#include "common.h"
+
+namespace w2v {
+
+// per-window normalisation statistics (lib/datautils.py:122-125) + valid encoder frames.
+// stats[b] = (mean, 1/std) over the zero-padded row of norm_len[b] samples; (0, 1) if norm_len==0.
+int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                        const int32_t* norm_len, int B, float2* stats, int32_t* enc_len,
+                        cudaStream_t s);
+
+// conv layer 0 (1->512, k=10, s=5) + LayerNorm(512) + GELU, input normalisation fused (HF:281-299).
+// out bf16 [B*R0, 512], channels-last.
+int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                         const float2* stats, const float* w_t /*[10][512]*/, const float* bias,
+                         const float* gamma, const float* beta, float eps, __nv_bfloat16* out,
+                         int B, int R0, cudaStream_t s);
+
+// LayerNorm over C (512 or 1024) per row, optional GELU; in fp32 or bf16, out bf16. in==out allowed
+// for bf16 input.
+int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const float* gamma,
+                     const float* beta, float eps, int act, __nv_bfloat16* out, cudaStream_t s);
+
+// h fp32 [B*R, C] -> zpad bf16 [B*(R+pad2), C] interior rows (64-row zero halo each side is
+// memset by the caller). Feeds the positional conv (HF:360-368).
+int cast_to_padded_launch(const float* h, int B, int R, int C, int halo, __nv_bfloat16* zpad,
+                          cudaStream_t s);
+
+// gather a strided fp32 [B, T, C] view into contiguous [B*T, C] (head entry point)
+int gather_rows_launch(const float* src, int64_t batch_stride, int B, int T, int C, float* dst,
+                       cudaStream_t s);
+
+// final LayerNorm(1024) + Linear(1024->1) + sigmoid + masking (lib/models.py:317-319,
+// lib/evaluate.py:82-91). logits/probs [B*R] (either may be null).
+int head_final_launch(const float* y, int B, int R, int C, const float* gamma, const float* beta,
+                      float eps, const float* w_out, const float* b_out, const int32_t* out_len,
+                      float* logits, float* probs, cudaStream_t s);
+
+// fused non-causal attention, key-length masked (HF:500-549; torch MHA in lib/models.py:291-300)
+int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
+                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s);
+
+// ---- weight packing -----------------------------------------------------------------------
+// dst_bf16[r*ld_dst + c] = src[r*cols + c] * scale
+int pack_matrix_launch(const float* src, int rows, int cols, float scale, __nv_bfloat16* dst,
+                       int64_t ld_dst, cudaStream_t s);
+// conv weight [O, I, J] fp32 -> [O, J*I] bf16 (K index = j*I + i), optional per-tap scale[j]
+int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_scale,
+                     __nv_bfloat16* dst, cudaStream_t s);
+// [O, J] fp32 -> [J, O] fp32 (conv layer 0 taps)
+int transpose_f32_launch(const float* src, int O, int J, float* dst, cudaStream_t s);
+// dst[i] = a[i] * sa + (b ? b[i] * sb : 0)
+int axpby_launch(const float* a, float sa, const float* b, float sb, float* dst, int n,
+                 cudaStream_t s);
+// weight-norm tap scale: scale[j] = g[j] / sqrt(sum_{o,i} v[o,i,j]^2)   (HF:355, dim=2)
+int weightnorm_scale_launch(const float* v, const float* g, int OI, int J, float* scale,
+                            cudaStream_t s);
+
+// ---- talk-level reductions (see w2vseg.h) ---------------------------------------------------
+int scatter_rows_launch(const float* rows, int64_t row_stride, const int32_t* start,
+                        const int32_t* count, int n_rows, double* talk, int64_t n_frames,
+                        cudaStream_t s);
+int nanfill_launch(double* talk, int64_t n_frames, const int32_t* idx, int n_idx, cudaStream_t s);
+int overlap_average_launch(const double* tilings, int n_tilings, int64_t n_frames, double* out,
+                           cudaStream_t s);
+int moving_average_launch(const double* arr, int64_t n, int window, double* out, cudaStream_t s);
+
+}  // namespace w2v
