@@ -1,0 +1,139 @@
+"""End-to-end parity of the CUDA SFC path (through the C ABI) against
+  (1) golden vectors produced by the UNMODIFIED reference (tests/golden/, oracle/make_golden.py), and
+  (2) the CPU oracle (oracle/sfc_oracle.py) on seeded inputs the goldens do not cover.
+
+Tolerance (BASELINE.json north_star): per-frame probabilities within max-abs 2e-2 of the
+reference's fp32 forward (the CUDA path computes GEMM/conv/attention operands in bf16 with fp32
+accumulation, fp32 residual stream / LayerNorm statistics / head).
+"""
+import numpy as np
+import pytest
+import torch
+
+from wav2vecsegmenter_b200 import synth
+
+from util import load_gold, make_batch, out_lens_ref, spec_of
+
+pytestmark = pytest.mark.gpu
+PROB_TOL = 2e-2
+
+_engines = {}
+
+
+def engine_for(spec, seed):
+    from wav2vecsegmenter_b200.engine import SFCEngine
+
+    key = (spec, seed)
+    if key not in _engines:
+        _engines.clear()  # one model resident at a time
+        e = SFCEngine(spec)
+        e.load_state_dict(synth.random_state_dict(spec, seed))
+        _engines[key] = e
+    return _engines[key]
+
+
+@pytest.mark.parametrize("name", ["tiny_batch", "middle_window", "middle_half_batch", "large_batch"])
+def test_probs_match_reference_golden(name):
+    g = load_gold(name)
+    spec = spec_of(g)
+    lens = [int(x) for x in g["lens"]]
+    eng = engine_for(spec, int(g["seed"]))
+    audio = make_batch(lens, int(g["audio_seed"])).cuda()
+    lmax = max(lens)
+    out_mask = torch.from_numpy(g["out_mask"])
+    out_len = out_mask.sum(1).tolist()
+    # fused path: normalisation over the padded batch row (norm_len = lmax for every window)
+    logits, probs = eng.sfc_forward(audio, lens, [lmax] * len(lens), out_len, lmax)
+    torch.cuda.synchronize()
+    T = out_mask.shape[1]
+    p = probs[:, :T].cpu().numpy()
+    l = logits[:, :T].cpu().numpy()
+    assert np.isfinite(p).all()
+    err = np.abs(p - g["probs"]).max()
+    assert err <= PROB_TOL, f"{name}: max-abs prob err {err}"
+    assert (p[~g["out_mask"]] == 0).all() and (l[~g["out_mask"]] == 0).all()
+    # frames the mask excludes beyond T stay zero too
+    assert (probs[:, T:].cpu().numpy() == 0).all()
+    # decisions at the 0.5 threshold (pDAC/pSTRM): at least 99 % identical
+    agree = ((p > 0.5) == (g["probs"] > 0.5))[g["out_mask"]].mean()
+    assert agree >= 0.99, f"{name}: only {agree:.4f} of frames on the same side of 0.5"
+
+
+@pytest.mark.parametrize("name", ["tiny_batch", "middle_half_batch"])
+def test_hidden_and_two_call_path_match_golden(name):
+    """model.wav2vec_model(...) then model.seg_model(...) as two calls (lib/evaluate.py:59,72)"""
+    g = load_gold(name)
+    spec = spec_of(g)
+    lens = [int(x) for x in g["lens"]]
+    eng = engine_for(spec, int(g["seed"]))
+    audio = make_batch(lens, int(g["audio_seed"])).cuda()
+    lmax = max(lens)
+    hidden, enc_len = eng.encode(audio, lens, [lmax] * len(lens), lmax)
+    T = int(g["hidden_T"])
+    assert hidden.shape[1] >= T
+    assert enc_len.tolist() == [eng.num_frames(n) for n in lens]
+    frames = g["hidden_frames"]
+    h = hidden[:, :T][:, frames].cpu().numpy()
+    ref = g["hidden"]
+    rel = np.abs(h - ref).max() / np.abs(ref).max()
+    assert rel < 2e-2, f"hidden rel err {rel}"
+    out_mask = torch.from_numpy(g["out_mask"])
+    Tm = out_mask.shape[1]
+    logits, probs = eng.head(hidden[:, :Tm], out_mask.sum(1).tolist())
+    torch.cuda.synchronize()
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= PROB_TOL
+
+
+def test_prenormalised_audio_path():
+    """audio already normalised by CollateFn (norm_len = 0) == on-device normalisation"""
+    g = load_gold("tiny_batch")
+    spec = spec_of(g)
+    lens = [int(x) for x in g["lens"]]
+    eng = engine_for(spec, int(g["seed"]))
+    raw = make_batch(lens, int(g["audio_seed"]))
+    norm = (raw - raw.mean(1, keepdim=True)) / raw.std(1, keepdim=True)
+    np.testing.assert_allclose(norm[:, :64].numpy(), g["audio_norm_head"], rtol=1e-5, atol=1e-6)
+    out_len = torch.from_numpy(g["out_mask"]).sum(1).tolist()
+    lmax = max(lens)
+    _, p0 = eng.sfc_forward(raw.cuda(), lens, [lmax] * 3, out_len, lmax)
+    _, p1 = eng.sfc_forward(norm.cuda(), lens, [0] * 3, out_len, lmax)
+    assert (p0 - p1).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("lens", [[48000], [35000, 64000, 16000 * 3 + 17, 400 * 40]])
+def test_probs_match_oracle_on_seeded_inputs(lens):
+    from oracle import sfc_oracle
+
+    spec = synth.TINY
+    sd = synth.random_state_dict(spec, 3)
+    eng = engine_for(spec, 3)
+    raw = make_batch(lens, 77)
+    lmax = max(lens)
+    out_len = out_lens_ref(lens)
+    T_hidden = sfc_oracle.conv_out_frames(lmax)
+    out_mask = torch.zeros(len(lens), max(out_len), dtype=torch.bool)
+    for i, n in enumerate(out_len):
+        out_mask[i, :n] = True
+    norm = sfc_oracle.normalize_rows(raw, [True] * len(lens))
+    with torch.no_grad():
+        ref_p, ref_l, ref_mask, _ = sfc_oracle.batch_probs(sd, norm, lens, out_mask, spec.keep_layers, spec.head_heads)
+    ol = ref_mask.sum(1).tolist()
+    _, probs = eng.sfc_forward(raw.cuda(), lens, [lmax] * len(lens), ol, lmax)
+    p = probs[:, : ref_mask.shape[1]].cpu()
+    assert (p - ref_p).abs().max().item() <= PROB_TOL
+    assert T_hidden <= eng.frame_stride(lmax) - 1
+
+
+def test_window_independent_of_batch_composition():
+    """a window's valid-frame probabilities do not depend on what else is in the device batch
+    (the property that lets windows shard across GPUs), given the same norm_len"""
+    spec = synth.TINY
+    eng = engine_for(spec, 3)
+    lens = [64000, 40000]
+    raw = make_batch(lens, 5)
+    ol = out_lens_ref(lens)
+    _, p_pair = eng.sfc_forward(raw.cuda(), lens, [64000, 64000], ol, 64000)
+    _, p_single = eng.sfc_forward(raw[1:, :40000].contiguous().cuda(), [40000], [64000], ol[1:], 40000)
+    a = p_pair[1, : ol[1]].cpu()
+    b = p_single[0, : ol[1]].cpu()
+    assert (a - b).abs().max().item() < 1e-5
