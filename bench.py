@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: SFC audio-seconds processed per second, large (24/24) + 24 adapters,
+batch 14 x 20 s windows, bf16 operands / fp32 accumulate, synthetic 16 kHz audio, random-init
+weights of that architecture (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of 14 windows (280 audio-seconds) per GPU.
+Prints ONE JSON line on rank 0 (see the driver contract in DESIGN.md §Measurement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 14
+WIN_SAMPLES = 320_000
+WIN_SEC = 20.0
+T_FRAMES = 999          # frames of one 20 s window
+CONV_T = [63999, 31999, 15999, 7999, 3999, 1999, 999]
+CONV_K = [10, 3, 3, 3, 3, 2, 2]
+
+
+def work_model(keep=24, adapters=24, D=1024, F=4096, A=512, HF=2048, T=T_FRAMES):
+    """algorithmic FLOPs per 20 s window (2 FLOP / MAC; bias, LN, GELU, softmax excluded) —
+    BASELINE.md §3 / SURVEY.md §8d. Returns (total, per-kernel-family dict)."""
+    fl = {}
+    fl["conv0"] = 2 * 1 * 512 * CONV_K[0] * CONV_T[0]
+    fl["gemm.conv_k3"] = sum(2 * 512 * 512 * 3 * CONV_T[l] for l in (1, 2, 3, 4))
+    fl["gemm.conv_k2"] = sum(2 * 512 * 512 * 2 * CONV_T[l] for l in (5, 6))
+    fl["gemm.feat_proj"] = 2 * T * 512 * D
+    fl["gemm.pos_conv"] = 2 * T * D * 64 * 128
+    fl["gemm.qkv"] = keep * 2 * T * D * 3 * D
+    fl["gemm.attn_out"] = keep * 2 * T * D * D
+    fl["attention_d64"] = keep * 4 * T * T * D
+    fl["gemm.ffn_up"] = keep * 2 * T * D * F + adapters * 2 * T * D * A
+    fl["gemm.ffn_down"] = keep * 2 * T * F * D + adapters * 2 * T * A * D
+    fl["gemm.head"] = 8 * T * D * D + 4 * T * D * HF
+    fl["attention_d128"] = 4 * T * T * D
+    fl["head_final"] = 2 * T * D
+    return sum(fl.values()), fl
+
+
+def read_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for nme, v in zip(names, r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from wav2vecsegmenter_b200 import _native as nat
+    from wav2vecsegmenter_b200 import synth
+    from wav2vecsegmenter_b200.engine import SFCEngine
+
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    spec = synth.LARGE_ALL
+    eng = SFCEngine(spec, dev)
+    eng.load_state_dict(synth.random_state_dict(spec, seed=0))
+    lib = eng.lib
+
+    # synthetic audio resident in HBM: several distinct batches, rotated, so no step re-reads the
+    # previous step's input; the per-step working set (~2.1 GB of activations) is >> 126 MB L2.
+    n_rot = 4
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    audio = [torch.randn(BATCH, WIN_SAMPLES, device=dev, generator=g) * 0.1 for _ in range(n_rot)]
+    lens = torch.full((BATCH,), WIN_SAMPLES, dtype=torch.int32, device=dev)
+    out_len = torch.full((BATCH,), T_FRAMES, dtype=torch.int32, device=dev)
+    R = eng.frame_stride(WIN_SAMPLES)
+    logits = torch.empty(BATCH, R, device=dev)
+    probs = torch.empty(BATCH, R, device=dev)
+    gathered = torch.empty(world * BATCH, R, device=dev) if world > 1 else None
+
+    def step(i):
+        eng.sfc_forward(audio[i % n_rot], lens, lens, out_len, WIN_SAMPLES, logits, probs)
+        if world > 1:  # the path's only exchange: per-frame probability rows to every rank
+            dist.all_gather_into_tensor(gathered, probs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.w2vseg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.w2vseg_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    audio_sec = world * BATCH * WIN_SEC * args.steps
+    value = audio_sec / (ms / 1e3)
+
+    # ---- end to end through the public host API: pinned host audio -> H2D -> forward -> D2H probs
+    host_audio = [a.cpu().pin_memory() for a in audio[:2]]
+    host_probs = torch.empty(BATCH, R).pin_memory()
+    dev_in = [torch.empty(BATCH, WIN_SAMPLES, device=dev) for _ in range(2)]
+    lens_host = [WIN_SAMPLES] * BATCH
+
+    def e2e_step(i):
+        # host -> device copy of this step's input, forward, device -> host read of its result
+        buf = dev_in[i % 2]
+        buf.copy_(host_audio[i % 2], non_blocking=True)
+        eng.sfc_forward(buf, lens, lens, out_len, WIN_SAMPLES, logits, probs)
+        host_probs.copy_(probs, non_blocking=True)
+
+    for i in range(max(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = audio_sec / (float(t.item()) / 1e3)
+
+    # ---- per-kernel device timing (CUDA events around every launch, on the launching stream)
+    roofline, kernels = None, None
+    cpu_baseline = None
+    if rank == 0:
+        lib.w2vseg_profile_enable(1)
+        prof_steps = min(3, args.steps)
+        for i in range(prof_steps):
+            eng.sfc_forward(audio[i % n_rot], lens, lens, out_len, WIN_SAMPLES, logits, probs)
+        buf = nat.C.create_string_buffer(1 << 16)
+        lib.w2vseg_profile_collect(buf, len(buf))
+        lib.w2vseg_profile_enable(0)
+        kernels = {}
+        for line in buf.value.decode().splitlines():
+            nme, cnt, tot = line.split()
+            kernels[nme] = {"launches_per_step": int(cnt) / prof_steps, "ms_per_step": float(tot) / prof_steps}
+        total_fl, fl = work_model()
+        peaks = read_peaks()
+        gemm_names = [k for k in kernels if k.startswith("gemm.") and k != "gemm.pos_conv"]
+        gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_names)
+        gemm_fl = sum(fl[k] for k in gemm_names) * BATCH
+        gemm_launches = sum(kernels[k]["launches_per_step"] for k in gemm_names)
+        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        traffic = None
+        tp = ROOT / "profiles" / "gemm_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        roofline = {
+            "kernel": "gemm_tc_kernel<256> (tcgen05/TMEM/TMA; all Linear + conv layers 1-6)",
+            "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
+            "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
+            "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
+            "traffic": traffic,
+            "launches_per_step": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
+            "algorithmic_gflop_per_step": round(gemm_fl / 1e9, 1),
+            "share_of_step": round(gemm_ms / sum(k["ms_per_step"] for k in kernels.values()), 4),
+            "whole_path_frac": round(value / world * (total_fl / WIN_SEC) / 1e12 / peaks["tflops_sustained"], 4),
+        }
+        for k, v in kernels.items():
+            if k in fl and v["ms_per_step"] > 0:
+                v["tflops"] = round(fl[k] * BATCH / (v["ms_per_step"] / 1e3) / 1e12, 1)
+            v["ms_per_step"] = round(v["ms_per_step"], 4)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_reference_timing(n_windows=1, reps=2)
+
+    if rank == 0:
+        line = {
+            "metric": "SFC audio-sec/sec (large 24/24)", "value": round(value, 1), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "large (24/24) + 24 FFN adapters SFC inference, batch 14 x 20 s windows per GPU per step",
+                       "global_batch_windows": world * BATCH, "window_samples": WIN_SAMPLES,
+                       "frames_per_window": T_FRAMES, "parallelism": f"dp{world} (windows sharded, NCCL all_gather of probability rows)" if world > 1 else "single GPU",
+                       "l2": "inputs rotate over 4 batches; per-step working set ~2.1 GB >> 126 MB L2",
+                       "weights": "random-init, seed 0"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": BATCH * WIN_SAMPLES * 4, "d2h_bytes_per_step": BATCH * R * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_timing(n_windows=1, reps=2):
+    """the reference's CPU path for the same model/config, timed on this box's host cores.
+    The reference itself (pure Python on HF transformers) cannot travel to the GPU box, so this
+    is its restatement (oracle/sfc_oracle.py, torch fp32 CPU kernels == what the reference runs),
+    kind "port"."""
+    import torch
+
+    from oracle import sfc_oracle
+    from wav2vecsegmenter_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = synth.LARGE_ALL
+    sd = synth.random_state_dict(spec, seed=0)
+    g = torch.Generator().manual_seed(99)
+    audio = torch.randn(n_windows, WIN_SAMPLES, generator=g)
+    audio = sfc_oracle.normalize_rows(audio, [True] * n_windows)
+    out_mask = torch.ones(n_windows, T_FRAMES, dtype=torch.bool)
+    times = []
+    with torch.no_grad():
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            sfc_oracle.batch_probs(sd, audio, [WIN_SAMPLES] * n_windows, out_mask, spec.keep_layers, spec.head_heads)
+            times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {"value": round(n_windows * WIN_SEC / best, 2), "unit": "audio-s/s", "cores": cores,
+            "kind": "port",
+            "sample": f"{n_windows} x 20 s window(s) of the same large(24/24)+adapters model, fp32 torch CPU, "
+                      f"best of {reps} after 1 warm-up ({best:.2f} s per pass)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import sfc_oracle
+    from wav2vecsegmenter_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = synth.LARGE_ALL
+    sd = synth.random_state_dict(spec, seed=0)
+    g = torch.Generator().manual_seed(99)
+    n_win = 1  # bounded sample: 1 of the 14 windows of a batch per step
+    audio = sfc_oracle.normalize_rows(torch.randn(n_win, WIN_SAMPLES, generator=g), [True] * n_win)
+    out_mask = torch.ones(n_win, T_FRAMES, dtype=torch.bool)
+    steps = min(args.steps, 8)
+    warm = min(args.warmup, 1)
+
+    def step():
+        with torch.no_grad():
+            sfc_oracle.batch_probs(sd, audio, [WIN_SAMPLES] * n_win, out_mask, spec.keep_layers, spec.head_heads)
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n_win * WIN_SEC * steps / dt
+    sample = (f"each step = {n_win} x 20 s window (bounded sample of the 14-window batch), fp32 torch CPU, "
+              f"{cores} threads; {steps} timed steps (capped from --steps {args.steps})")
+    line = {
+        "impl": "reference", "metric": "SFC audio-sec/sec (large 24/24)", "value": round(value, 2),
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": round(dt / steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "large (24/24) + 24 FFN adapters SFC inference, batch 14 x 20 s windows per GPU per step",
+                   "weights": "random-init, seed 0"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,12 @@ int64_t w2vseg_launch_count(void);
 /* 0 if the current CUDA device is an sm_100 part this library can run on, else W2VSEG_ERR_CUDA */
 int32_t w2vseg_device_ok(void);
 
+/* Per-kernel device timing for the roofline report: when enabled every kernel this library
+ * launches is bracketed by CUDA events on its stream. collect() synchronises the device and
+ * writes "<kernel-name> <launches> <total_ms>\n" lines into buf; returns bytes written. */
+int32_t w2vseg_profile_enable(int32_t on);
+int64_t w2vseg_profile_collect(char* buf, size_t cap);
+
 /* ---- geometry (pure host arithmetic) ------------------------------------------------------- */
 /* conv-stack output length for `n_samples` input samples (HF:1005-1024); 0 if n_samples < 400 */
 int32_t w2vseg_num_frames(int64_t n_samples);

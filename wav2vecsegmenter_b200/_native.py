@@ -49,6 +49,8 @@ SIGNATURES = {
     "w2vseg_last_error": (C.c_char_p, []),
     "w2vseg_launch_count": (_I64, []),
     "w2vseg_device_ok": (_I32, []),
+    "w2vseg_profile_enable": (_I32, [_I32]),
+    "w2vseg_profile_collect": (_I64, [C.c_char_p, _SZ]),
     "w2vseg_num_frames": (_I32, [_I64]),
     "w2vseg_frame_stride": (_I32, [_I64]),
     "w2vseg_create": (_I32, [C.POINTER(Config), C.POINTER(_P)]),

@@ -263,6 +263,7 @@ int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((R + ATT_BQ - 1) / ATT_BQ, heads, B);
   const int smem = 5 * ATT_BKV * head_dim * 2;
+  ProfScope ps(s, head_dim == 64 ? "attention_d64" : "attention_d128");
   if (head_dim == 64) {
     attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
   } else {

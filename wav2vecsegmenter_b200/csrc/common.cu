@@ -3,7 +3,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace w2v {
 
@@ -78,9 +81,71 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return 0;
 }
 
+// ---- profiling -----------------------------------------------------------------------------
+namespace {
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+thread_local const char* g_prof_tag = nullptr;
+}  // namespace
+
+bool prof_enabled() { return g_prof_on; }
+void prof_tag(const char* tag) { g_prof_tag = tag; }
+
+ProfScope::ProfScope(cudaStream_t s, const char* default_name) : stream(s), slot(-1) {
+  const char* name = g_prof_tag ? g_prof_tag : default_name;
+  g_prof_tag = nullptr;
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
 }  // namespace w2v
 
 extern "C" {
+
+int32_t w2vseg_profile_enable(int32_t on) {
+  w2v::g_prof_on = on != 0;
+  return 0;
+}
+
+// Synchronises, then writes one line per kernel name: "<name> <launches> <total_ms>\n".
+// Returns the number of bytes written (excluding the terminating NUL) or a negative error.
+int64_t w2vseg_profile_collect(char* buf, size_t cap) {
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    w2v::set_error("profile_collect: device synchronize failed");
+    return W2VSEG_ERR_CUDA;
+  }
+  std::map<std::string, std::pair<long long, double>> acc;
+  std::vector<std::string> order;
+  for (auto& r : w2v::g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    auto it = acc.find(r.name);
+    if (it == acc.end()) { order.push_back(r.name); acc[r.name] = {1, (double)ms}; }
+    else { it->second.first += 1; it->second.second += ms; }
+  }
+  w2v::g_prof.clear();
+  size_t off = 0;
+  for (auto& n : order) {
+    char line[256];
+    int k = snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), acc[n].first, acc[n].second);
+    if (off + (size_t)k + 1 > cap) break;
+    memcpy(buf + off, line, (size_t)k);
+    off += (size_t)k;
+  }
+  if (cap > 0) buf[off < cap ? off : cap - 1] = 0;
+  return (int64_t)off;
+}
 
 int32_t w2vseg_abi_version(void) { return W2VSEG_ABI_VERSION; }
 const char* w2vseg_last_error(void) { return w2v::g_err; }

@@ -59,4 +59,16 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
 
 int num_sms();
 
+// ---- optional per-kernel timing (bench.py roofline numbers; off by default) -------------------
+// When enabled, every launcher brackets its kernel with CUDA events on the launching stream.
+// The engine names the next launch with prof_tag(); launchers fall back to their own name.
+bool prof_enabled();
+void prof_tag(const char* tag);  // applies to the next ProfScope only
+struct ProfScope {
+  ProfScope(cudaStream_t s, const char* default_name);
+  ~ProfScope();
+  cudaStream_t stream;
+  int slot;
+};
+
 }  // namespace w2v

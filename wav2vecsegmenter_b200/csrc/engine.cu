@@ -300,7 +300,9 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.conv[l - 1], rows_out, kConvK[l] * CD, h->conv_w[l], CD, h->conv_b[l]);
     g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
     g.out = w.conv[l]; g.ld_out = CD;
+    prof_tag(kConvK[l] == 3 ? "gemm.conv_k3" : "gemm.conv_k2");
     W2V_TRY(gemm_tc_launch(g, 256, st));
+    prof_tag("ln_gelu.conv");
     W2V_TRY(layernorm_launch(w.conv[l], false, rows_out, CD, h->conv_ln[l].g, h->conv_ln[l].b,
                              c.ln_eps, /*gelu*/ 1, w.conv[l], st));
   }
@@ -311,6 +313,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.feat, M, CD, h->fp_w, D, h->fp_b);
     g.out = w.h; g.ld_out = D; g.out_f32 = 1;
     g.mask_len = w.enc_len; g.mask_period = R;
+    prof_tag("gemm.feat_proj");
     W2V_TRY(gemm_tc_launch(g, 256, st));
   }
 
@@ -328,6 +331,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     g.bias = h->pos_b; g.act_split = D; g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
     g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
     g.mask_len = nullptr; g.mask_period = 1;
+    prof_tag("gemm.pos_conv");
     W2V_TRY(gemm_tc_launch(g, 64, st));
   }
 
@@ -338,6 +342,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
       g.out = w.qkv; g.ld_out = 3 * D;
+      prof_tag("gemm.qkv");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     W2V_TRY(attention_launch(w.qkv, B, R, c.heads, h->DH, w.enc_len, 1.0f / sqrtf((float)h->DH),
@@ -345,6 +350,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      prof_tag("gemm.attn_out");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln2.g, L.ln2.b, c.ln_eps, 0, w.xn, st));
@@ -352,11 +358,13 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       GemmProblem g = linear(w.xn, M, D, L.w1, L.F1, L.b1);
       g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
       g.out = w.mid; g.ld_out = L.F1;
+      prof_tag("gemm.ffn_up");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     {
       GemmProblem g = linear(w.mid, M, L.F1, L.w2, D, L.b2);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      prof_tag("gemm.ffn_down");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
   }
@@ -376,12 +384,14 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     {
       GemmProblem g = linear(w.xn, M, D, H.win, 3 * D, H.bin);
       g.out = w.qkv; g.ld_out = 3 * D;
+      prof_tag("gemm.head");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     W2V_TRY(attention_launch(w.qkv, B, R, c.head_heads, hd, out_len, 1.0f / sqrtf((float)hd), w.ctx, st));
     {
       GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      prof_tag("gemm.head");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     W2V_TRY(layernorm_launch(y, true, M, D, H.ln2.g, H.ln2.b, c.ln_eps, 0, w.xn, st));
@@ -389,11 +399,13 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       GemmProblem g = linear(w.xn, M, D, H.w1, c.head_ffn, H.b1);
       g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
       g.out = w.mid; g.ld_out = c.head_ffn;
+      prof_tag("gemm.head");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
     {
       GemmProblem g = linear(w.mid, M, c.head_ffn, H.w2, D, H.b2);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      prof_tag("gemm.head");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
   }

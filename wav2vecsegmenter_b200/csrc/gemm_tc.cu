@@ -283,7 +283,10 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
       (long long)a.num_groups * a.tiles_m_per_group * (g.N / BLOCK_N);
   if (num_tiles == 0) return 0;
   const int grid = (int)(num_tiles < (long long)num_sms() ? num_tiles : (long long)num_sms());
-  gemm_tc_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+  {
+    ProfScope ps(stream, BLOCK_N == 256 ? "gemm_bn256" : (BLOCK_N == 128 ? "gemm_bn128" : "gemm_bn64"));
+    gemm_tc_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+  }
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -464,6 +464,7 @@ int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t*
                         const int32_t* norm_len, int B, float2* stats, int32_t* enc_len,
                         cudaStream_t s) {
   if (B <= 0) return 0;
+  ProfScope ps(s, "window_stats");
   window_stats_kernel<<<B, 1024, 0, s>>>(audio, audio_stride, sample_len, norm_len, stats, enc_len);
   W2V_CHECK_LAUNCH();
   return 0;
@@ -475,6 +476,7 @@ int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t
                          int B, int R0, cudaStream_t s) {
   if (B <= 0 || R0 <= 0) return 0;
   dim3 grid((R0 + C0_ROWS - 1) / C0_ROWS, B);
+  ProfScope ps(s, "conv0_ln_gelu");
   conv0_ln_gelu_kernel<<<grid, C0_THREADS, 0, s>>>(audio, audio_stride, sample_len, stats, w_t,
                                                    bias, gamma, beta, eps, out, R0);
   W2V_CHECK_LAUNCH();
@@ -485,6 +487,7 @@ int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const flo
                      const float* beta, float eps, int act, __nv_bfloat16* out, cudaStream_t s) {
   if (rows <= 0) return 0;
   const unsigned grid = blocks_for(rows, 8);
+  ProfScope ps(s, act ? "layernorm_gelu" : "layernorm");
 #define W2V_LN(Cv, F32, ACTv)                                                                  \
   layernorm_kernel<Cv, F32, ACTv><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, out)
   if (C == 512 && !in_f32 && act == 0) W2V_LN(512, false, 0);
@@ -505,6 +508,7 @@ int cast_to_padded_launch(const float* h, int B, int R, int C, int halo, __nv_bf
                           cudaStream_t s) {
   const long long total = (long long)B * R * C / 4;
   if (total <= 0) return 0;
+  ProfScope ps(s, "cast_to_padded");
   cast_to_padded_kernel<<<blocks_for(total, 256), 256, 0, s>>>(h, R, C, halo, zpad, total);
   W2V_CHECK_LAUNCH();
   return 0;
@@ -514,6 +518,7 @@ int gather_rows_launch(const float* src, int64_t batch_stride, int B, int T, int
                        cudaStream_t s) {
   const long long total = (long long)B * T * C / 4;
   if (total <= 0) return 0;
+  ProfScope ps(s, "gather_rows");
   gather_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, batch_stride, T, C, dst, total);
   W2V_CHECK_LAUNCH();
   return 0;
@@ -525,6 +530,7 @@ int head_final_launch(const float* y, int B, int R, int C, const float* gamma, c
   W2V_REQUIRE(C == 1024, "head_final: hidden size %d unsupported (1024 only)", C);
   const long long rows = (long long)B * R;
   if (rows <= 0) return 0;
+  ProfScope ps(s, "head_final");
   head_final_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(y, rows, R, gamma, beta, eps, w_out, b_out,
                                                         out_len, logits, probs);
   W2V_CHECK_LAUNCH();
