@@ -1,0 +1,33 @@
+"""ncu target: the three dominant GEMM shapes of the large (24/24) model at batch 14, a few
+launches each (run plain first, then under ncu — see profiles/README)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from wav2vecsegmenter_b200 import _native as n  # noqa: E402
+
+lib = n.load()
+M = 14000
+shapes = [("ffn_up", 4608, 1024, 1, 0), ("ffn_down", 1024, 4608, 0, 1), ("qkv", 3072, 1024, 0, 0)]
+g = torch.Generator(device="cuda").manual_seed(0)
+for name, N, K, act, f32 in shapes:
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / 32).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if f32 else None
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    for _ in range(3):
+        n.check(lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out),
+                                f32, 256, n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out), f32, 256,
+                        n.current_stream_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"{name}: M={M} N={N} K={K} {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s")

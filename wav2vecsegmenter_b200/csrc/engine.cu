@@ -59,7 +59,7 @@ struct Slot {
 };
 
 struct Workspace {
-  float2* stats; int32_t* enc_len;
+  float2* stats; int32_t* enc_len; double2* stat_partial;
   bf16* conv[7];
   bf16* feat; float* h; bf16* zpad; bf16* xn; bf16* qkv; bf16* ctx; bf16* mid;
   size_t bytes;
@@ -241,6 +241,7 @@ Workspace carve(const w2vseg_handle* h, uint8_t* base, int B, int R) {
   const int D = h->D, CD = h->cfg.conv_dim;
   w.stats = reinterpret_cast<float2*>(take(sizeof(float2) * B));
   w.enc_len = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * B));
+  w.stat_partial = reinterpret_cast<double2*>(take(sizeof(double2) * 64 * B));
   for (int l = 0; l < 7; ++l) {
     const size_t rows = M << (6 - l);
     w.conv[l] = reinterpret_cast<bf16*>(take((rows + 4) * CD * sizeof(bf16)));
@@ -287,7 +288,8 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
   const int D = h->D, CD = c.conv_dim;
   const int64_t M = (int64_t)B * R;
 
-  W2V_TRY(window_stats_launch(audio, audio_stride, sample_len, norm_len, B, w.stats, w.enc_len, st));
+  W2V_TRY(window_stats_launch(audio, audio_stride, sample_len, norm_len, B, w.stat_partial, w.stats,
+                              w.enc_len, st));
 
   // conv feature extractor (HF:382-419). Layer l activations: channels-last bf16 [B*R*2^(6-l), 512].
   const int R0 = R << 6;

@@ -3,9 +3,10 @@
 // CTA = 6 warps, one CTA per SM (persistent, static round-robin over output tiles):
 //   warp 0      TMA producer     (one lane): A tile 128x64 + W tile BLOCK_Nx64 per stage
 //   warp 1      MMA issuer       (one lane): 4 x tcgen05.mma (K=16) per stage, commit -> empty[]
-//   warps 2..5  epilogue         (128 threads = 128 accumulator rows): tcgen05.ld -> bias/act/
-//                                 residual -> global. TMEM holds TWO accumulators so the epilogue
-//                                 of tile i overlaps the MMAs of tile i+1.
+//   warps 2..9  epilogue         (8 warps: 4 TMEM lane quarters x 2 column halves; thread = one
+//                                 accumulator row): tcgen05.ld -> bias/act/residual -> global.
+//                                 TMEM holds TWO accumulators so the epilogue of tile i overlaps
+//                                 the MMAs of tile i+1.
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -17,7 +18,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;              // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -44,13 +45,7 @@ struct KernelArgs {
   int mask_period;
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == ACT_GELU) return gelu_erf(x);
-  if (act == ACT_RELU) return fmaxf(x, 0.f);
-  return x;
-}
-
-template <int BLOCK_N>
+template <int BLOCK_N, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const KernelArgs p) {
@@ -84,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -153,8 +148,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // 8 warps: warp w reads TMEM lane quarter (w & 3) — the only one it may touch — and the
+    // column half (w - 2) >> 2 of the tile. Thread = one accumulator row, 32 columns per step;
+    // the tcgen05.ld (and the residual read) of step c+1 is in flight while step c is processed.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = BLOCK_N / 2;       // columns per warp
+    constexpr int NCHUNK = COLS / 32;
     const int r_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -172,21 +173,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int t = (int)(orow - w * p.mask_period);
         zero_row = t >= __ldg(p.mask_len + w);
       }
+      const int colbase = nb * BLOCK_N + half * COLS;
+      const bool use_resid = OUT_F32 && p.resid != nullptr && row_ok;
+      const float4* r4 = use_resid
+          ? reinterpret_cast<const float4*>(p.resid + orow * p.ld_resid + colbase) : nullptr;
+
+      float4 res[2][8];
+      if (OUT_F32 && use_resid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[0][j] = r4[j];
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) +
+                              (uint32_t)(acc * BLOCK_N + half * COLS);
+      uint32_t raw[2][32];
+      tmem_ld_32x32b_x32(t_base, raw[0]);
 
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(t_base + (uint32_t)(c * 32), raw);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
         tc_wait_ld();
-        const int col0 = nb * BLOCK_N + c * 32;
+        if (c + 1 < NCHUNK) {
+          tmem_ld_32x32b_x32(t_base + (uint32_t)((c + 1) * 32), raw[(c + 1) & 1]);
+          if (OUT_F32 && use_resid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) res[(c + 1) & 1][j] = r4[(c + 1) * 8 + j];
+          }
+        }
+        const int col0 = colbase + c * 32;
         const int act = (col0 < p.act_split) ? p.act_lo : p.act_hi;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -195,32 +214,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
-        if (act != ACT_NONE) {
+        if (act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], act);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (zero_row) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         if (row_ok) {
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + col0;
-            if (p.resid != nullptr) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.resid + orow * p.ld_resid + col0);
+          if constexpr (OUT_F32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                   orow * p.ld_out + col0);
+            if (use_resid) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 r = r4[j];
+                const float4 r = res[c & 1][j];
                 v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
-            float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ld_out + col0;
-            uint4* o4 = reinterpret_cast<uint4*>(o);
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                 orow * p.ld_out + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
@@ -274,7 +295,10 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>,
+    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
@@ -285,7 +309,10 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
   const int grid = (int)(num_tiles < (long long)num_sms() ? num_tiles : (long long)num_sms());
   {
     ProfScope ps(stream, BLOCK_N == 256 ? "gemm_bn256" : (BLOCK_N == 128 ? "gemm_bn128" : "gemm_bn64"));
-    gemm_tc_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+    if (g.out_f32)
+      gemm_tc_kernel<BLOCK_N, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+    else
+      gemm_tc_kernel<BLOCK_N, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
   }
   W2V_CHECK_LAUNCH();
   return 0;

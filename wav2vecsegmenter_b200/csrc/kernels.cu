@@ -35,34 +35,56 @@ __device__ __forceinline__ double block_sum_f64(double v, double* sh) {
   return t;  // every thread holds the block total
 }
 
-__global__ void __launch_bounds__(1024)
-window_stats_kernel(const float* __restrict__ audio, long long audio_stride,
-                    const int* __restrict__ sample_len, const int* __restrict__ norm_len,
-                    float2* __restrict__ stats, int* __restrict__ enc_len) {
+// pass 1: grid (STAT_CHUNKS, B) — fp64 partial sums of x and x^2 over one slice of the window,
+// written (not atomically added) so the final sum order is fixed => bit-reproducible statistics
+constexpr int STAT_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+window_stats_partial_kernel(const float* __restrict__ audio, long long audio_stride,
+                            const int* __restrict__ sample_len, const int* __restrict__ norm_len,
+                            double2* __restrict__ partial) {
   __shared__ double sh[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int len = sample_len[b];
+  double s = 0.0, q = 0.0;
+  if (norm_len[b] > 0) {
+    const float* x = audio + (long long)b * audio_stride;
+    const int per = (len + STAT_CHUNKS - 1) / STAT_CHUNKS;
+    const int lo = blockIdx.x * per;
+    const int hi = min(len, lo + per);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const double v = (double)x[i];
+      s += v;
+      q += v * v;
+    }
+  }
+  s = block_sum_f64(s, sh);
+  q = block_sum_f64(q, sh);
+  if (threadIdx.x == 0) partial[b * STAT_CHUNKS + blockIdx.x] = make_double2(s, q);
+}
+
+// pass 2: one thread per window. mean = sum/nl ; var = (sum_sq - nl*mean^2)/(nl-1) over the
+// zero-padded row of nl samples (zeros add nothing to either sum).
+__global__ void window_stats_final_kernel(const double2* __restrict__ partial,
+                                          const int* __restrict__ sample_len,
+                                          const int* __restrict__ norm_len, int B,
+                                          float2* __restrict__ stats, int* __restrict__ enc_len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (enc_len != nullptr) enc_len[b] = conv_frames(sample_len[b]);
   const int nl = norm_len[b];
-  if (threadIdx.x == 0 && enc_len != nullptr) enc_len[b] = conv_frames(len);
   if (nl <= 0) {
-    if (threadIdx.x == 0) stats[b] = make_float2(0.f, 1.f);
+    stats[b] = make_float2(0.f, 1.f);
     return;
   }
-  const float* x = audio + (long long)b * audio_stride;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) s += (double)x[i];
-  const double mean = block_sum_f64(s, sh) / (double)nl;
-  double q = 0.0;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    const double d = (double)x[i] - mean;
-    q += d * d;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < STAT_CHUNKS; ++c) {
+    const double2 p = partial[b * STAT_CHUNKS + c];
+    s += p.x;
+    q += p.y;
   }
-  double ss = block_sum_f64(q, sh);
-  ss += (double)(nl - len) * mean * mean;  // the zero padding is part of the reference's row
-  if (threadIdx.x == 0) {
-    const double var = ss / (double)(nl - 1);
-    stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var)));
-  }
+  const double mean = s / (double)nl;
+  const double var = (q - (double)nl * mean * mean) / (double)(nl - 1);
+  stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var)));
 }
 
 // =============================================================================================
@@ -461,11 +483,15 @@ inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 
 
 // ---------------------------------------------------------------------------------------------
 int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
-                        const int32_t* norm_len, int B, float2* stats, int32_t* enc_len,
-                        cudaStream_t s) {
+                        const int32_t* norm_len, int B, double2* partial, float2* stats,
+                        int32_t* enc_len, cudaStream_t s) {
   if (B <= 0) return 0;
   ProfScope ps(s, "window_stats");
-  window_stats_kernel<<<B, 1024, 0, s>>>(audio, audio_stride, sample_len, norm_len, stats, enc_len);
+  window_stats_partial_kernel<<<dim3(STAT_CHUNKS, B), 256, 0, s>>>(audio, audio_stride, sample_len,
+                                                                  norm_len, partial);
+  W2V_CHECK_LAUNCH();
+  window_stats_final_kernel<<<(B + 127) / 128, 128, 0, s>>>(partial, sample_len, norm_len, B, stats,
+                                                            enc_len);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -8,8 +8,8 @@ namespace w2v {
 // per-window normalisation statistics (lib/datautils.py:122-125) + valid encoder frames.
 // stats[b] = (mean, 1/std) over the zero-padded row of norm_len[b] samples; (0, 1) if norm_len==0.
 int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
-                        const int32_t* norm_len, int B, float2* stats, int32_t* enc_len,
-                        cudaStream_t s);
+                        const int32_t* norm_len, int B, double2* partial /*[B*64] scratch*/,
+                        float2* stats, int32_t* enc_len, cudaStream_t s);
 
 // conv layer 0 (1->512, k=10, s=5) + LayerNorm(512) + GELU, input normalisation fused (HF:281-299).
 // out bf16 [B*R0, 512], channels-last.
