@@ -1,0 +1,220 @@
+"""GPU: whole-talk path (window plan -> CUDA forward -> scatter / NaN fill / tiling average ->
+segmentation -> yaml) against golden vectors produced by the reference's own pipeline
+(dataset -> DataLoader -> CollateFn -> infer -> pdac/strm/pthr -> update_yaml_content)."""
+import importlib
+import sys
+import wave
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from wav2vecsegmenter_b200 import synth
+
+from util import load_gold, spec_of
+
+pytestmark = pytest.mark.gpu
+PROB_TOL = 2e-2
+
+ALGOS = {
+    "dac": dict(max_segment_length=16, min_segment_length=0.2, threshold=0.5),
+    "strm": dict(max_segment_length=18, min_segment_length=0.2, min_pause_length=0.2, threshold=0.5),
+    "pthr": dict(max_segment_length=28, min_segment_length=0.2, max_lerp_range=4, min_lerp_range=0.4,
+                 threshold=0.1, moving_average_window=0.1),
+}
+
+
+def pcm_wave(n, seed):
+    x = synth.synthetic_audio(n, seed)
+    pcm = torch.round(x * 32767.0).clamp(-32768, 32767).to(torch.int16)
+    return pcm.numpy(), (pcm.float() / 32768.0).numpy()
+
+
+@pytest.fixture(scope="module")
+def seg():
+    for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+        del sys.modules[k]
+    return importlib.import_module("lib.segment")
+
+
+@pytest.fixture(scope="module")
+def tiny_engine():
+    from wav2vecsegmenter_b200.engine import SFCEngine
+
+    e = SFCEngine(synth.TINY)
+    e.load_state_dict(synth.random_state_dict(synth.TINY, 0))
+    return e
+
+
+def boundary_agreement(a, b, tol=1.0):
+    """fraction of reference boundaries (segment starts and ends, frames) reproduced within tol"""
+    if len(b) == 0:
+        return 1.0 if len(a) == 0 else 0.0
+    ref = np.asarray(b).reshape(-1)
+    got = np.asarray(a).reshape(-1)
+    if got.size == 0:
+        return 0.0
+    return float(np.mean([np.abs(got - r).min() <= tol for r in ref]))
+
+
+@pytest.mark.parametrize("name", ["tiny_talk", "tiny_talk_x1"])
+def test_talk_probs_and_segments(name, tiny_engine, seg):
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    g = load_gold(name)
+    _, wave_f = pcm_wave(int(g["n_samples"]), int(g["audio_seed"]))
+    it = int(g["inference_times"])
+    runner = TalkRunner(tiny_engine, batch_size=int(g["batch_size"]), segment_sec=20, inference_times=it)
+    res = runner.run([wave_f])[0]
+    assert len(res.probs) == int(g["duration_outframes"])
+    for i in range(it):
+        assert not np.isnan(res.per_tiling[i]).any()
+        err = np.abs(res.per_tiling[i] - g[f"probs_{i}"]).max()
+        assert err <= PROB_TOL, f"tiling {i}: {err}"
+    assert np.abs(res.probs - g["probs_avg"]).max() <= PROB_TOL
+    # device batching must not matter: other device batch sizes give the same probabilities
+    for db in (1, 5):
+        r2 = TalkRunner(tiny_engine, batch_size=int(g["batch_size"]), segment_sec=20, inference_times=it,
+                        device_batch=db).run([wave_f])[0]
+        assert np.abs(r2.probs - res.probs).max() < 1e-5
+    # segmentation algorithms on the reference's probabilities: bit-compatible yaml
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+        segs = fn(g["probs_avg"], **ALGOS[tag])
+        text = yaml.dump(seg.update_yaml_content([], segs, "talk.wav"), default_flow_style=True)
+        assert text == str(g[f"{tag}_yaml"]), tag
+    # ... and on the CUDA path's probabilities: boundaries agree (random-init weights: report)
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+        segs = fn(res.probs, **ALGOS[tag])
+        got = np.array([[s.start, s.end] for s in segs]).reshape(-1, 2)
+        agree = boundary_agreement(got, g[f"{tag}_bounds"])
+        print(f"{name} {tag}: {len(segs)} segments vs {len(g[tag + '_bounds'])}, boundary agreement {agree:.3f}")
+        assert agree >= 0.9, (tag, agree)
+
+
+def test_dropin_modules_match_reference(tmp_path, tiny_engine):
+    """the reference's own call sequence (segment.py:71-108) on the drop-in lib.* modules"""
+    from torch.utils.data import DataLoader
+
+    for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+        del sys.modules[k]
+    from lib.datautils import CollateFn
+    from lib.dataset import FixedSegmentationDatasetNoTarget
+    from lib.evaluate import infer
+    from lib.models import SHAS
+
+    g = load_gold("tiny_talk")
+    pcm, _ = pcm_wave(int(g["n_samples"]), int(g["audio_seed"]))
+    wav = tmp_path / "talk.wav"
+    with wave.open(str(wav), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    spec = spec_of(g)
+    model = SHAS("facebook/wav2vec2-xls-r-300m", spec.keep_layers, True, spec.adapter_layers, False, False,
+                 True, spec.head_layers, spec.head_heads, 0.1).to(torch.device("cuda:0"))
+    model.load_state_dict(synth.random_state_dict(spec, int(g["seed"])))
+    model.eval()
+    it = int(g["inference_times"])
+    ds = FixedSegmentationDatasetNoTarget(wav, 20, it)
+    assert ds.duration_outframes == int(g["duration_outframes"])
+    acc = None
+    for i in range(it):
+        ds.fixed_length_segmentation(i)
+        assert list(ds.starts) == list(g[f"starts_{i}"]) and list(ds.ends) == list(g[f"ends_{i}"])
+        dl = DataLoader(ds, batch_size=int(g["batch_size"]), num_workers=0, shuffle=False, collate_fn=CollateFn(0))
+        probs, logits, _, _ = infer(model, dl, torch.device("cuda:0"), False, "bce", None)
+        assert np.abs(probs - g[f"probs_{i}"]).max() <= PROB_TOL
+        acc = probs.copy() if acc is None else acc + probs
+    acc /= it
+    assert np.abs(acc - g["probs_avg"]).max() <= PROB_TOL
+
+
+def test_talk_reduction_kernels_bit_exact(tiny_engine):
+    """scatter / NaN fill / tiling average / moving average == the host oracle, bit for bit"""
+    from oracle import host_oracle as ho
+
+    eng = tiny_engine
+    rng = np.random.default_rng(0)
+    n = 3351
+    rows = torch.from_numpy(rng.random((5, 1100), dtype=np.float32)).cuda()
+    start = [0, 999, 1998, 2997, 3200]
+    count = [998, 999, -999, 200, 0]          # a gap at 998, a silent window, uncovered tail
+    talk = eng.scatter_rows(rows, start, count, n)
+    ref = np.full(n, np.nan)
+    rc = rows.cpu().numpy()
+    for w, (s, c) in enumerate(zip(start, count)):
+        if c > 0:
+            ref[s:s + c] = rc[w, :c]
+        elif c < 0:
+            ref[s:s - c] = 0
+    got = talk.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    nan_idx = np.flatnonzero(np.isnan(ref))
+    eng.nanfill(talk, nan_idx)
+    ho.nan_fill(ref)
+    np.testing.assert_array_equal(talk.cpu().numpy(), ref)
+
+    tilings = rng.random((3, 20011))
+    avg = eng.overlap_average(torch.from_numpy(tilings).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(avg, ho.average_tilings([t for t in tilings]))
+
+    g = load_gold("algos")
+    for c in range(int(g["n_cases"])):
+        p = g[f"p_{c}"]
+        w = int(g[f"maw_{c}"])
+        out = eng.moving_average(torch.from_numpy(p).cuda(), w).cpu().numpy()
+        np.testing.assert_array_equal(out, g[f"ma_{c}"], err_msg=f"moving average case {c} (window {w})")
+    # full size of the 2 h long-form config: N = 359 640 frames, window 5
+    big = rng.random(359_640)
+    out = eng.moving_average(torch.from_numpy(big).cuda(), 5).cpu().numpy()
+    c = np.concatenate([[0.0], big])
+    idx = rng.integers(5, len(big), 2000)
+    for i in idx:
+        s = 0.0
+        for k in range(i - 4, i + 1):
+            s += big[k]
+        assert out[i] == s / 5
+
+
+def test_pthr_with_gpu_moving_average_matches_reference(seg):
+    g = load_gold("algos")
+    checked = 0
+    for c in range(int(g["n_cases"])):
+        kw = yaml.safe_load(str(g[f"pthr_kw_{c}"]))
+        if kw["moving_average_window"] <= 0:
+            continue
+        segs = seg.pthr(g[f"p_{c}"], **kw)
+        text = yaml.dump(seg.update_yaml_content([], segs, "a.wav"), default_flow_style=True)
+        assert text == str(g[f"pthr_yaml_{c}"]), c
+        checked += 1
+    assert checked > 5
+
+
+def test_segment_cli_generate(tmp_path):
+    """segment.py generate(): checkpoint + config -> yaml records"""
+    for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.") or k == "segment"]:
+        del sys.modules[k]
+    import segment as cli
+    from wav2vecsegmenter_b200 import config as cfglib
+
+    spec = synth.TINY
+    pcm, _ = pcm_wave(400_000, 3)
+    wav = tmp_path / "a.wav"
+    with wave.open(str(wav), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    torch.save({"state_dict": synth.random_state_dict(spec, 0)}, tmp_path / "ckpt.pt")
+    (tmp_path / "train.yaml").write_text(yaml.dump({"task": {"autoregression": False, "vocab": None, "model": {
+        "_target_": "lib.models.SHAS", "wav2vec_model_name": "x", "wav2vec_keep_layers": spec.keep_layers,
+        "finetune_wav2vec": True, "wav2vec_ft_layers": spec.adapter_layers, "finetune_w2v_feat_enc": False,
+        "finetune_w2v_ffn": False, "ffn_adapter": True, "n_transformer_enc_layers": 1,
+        "n_transformer_enc_heads": 8, "init_dropout": 0.1}, "loss": {"tag": "bce"}}}))
+    (tmp_path / "orig.yaml").write_text(yaml.dump([{"wav": "a.wav", "offset": 0.0, "duration": 1.0}]))
+    cfg = cfglib.compose(cli.ROOT / "conf", "segment", [
+        f"ckpt_path={tmp_path / 'ckpt.pt'}", f"config_path={tmp_path / 'train.yaml'}", f"output_dir={tmp_path}",
+        "algorithm=pthr", "infer_data=custom", f"infer_data.wav_dir={tmp_path}",
+        f"infer_data.orig_seg_yaml={tmp_path / 'orig.yaml'}", "inference_times=2"])
+    content = cli.generate(cfg)
+    assert len(content) > 0 and set(content[0]) == {"duration", "offset", "rW", "uW", "speaker_id", "wav"}
+    text = yaml.dump(content, default_flow_style=True)
+    assert text.startswith("- {duration:")

@@ -152,6 +152,9 @@ const char* w2vseg_last_error(void) { return w2v::g_err; }
 int64_t w2vseg_launch_count(void) { return w2v::g_launches.load(std::memory_order_relaxed); }
 
 int32_t w2vseg_device_ok(void) {
+  static int cached_dev = -1;  // cudaGetDeviceProperties costs milliseconds: ask once per device
+  int cur = -2;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == cached_dev) return 0;
   int dev = 0;
   cudaDeviceProp prop;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
@@ -163,6 +166,7 @@ int32_t w2vseg_device_ok(void) {
                    prop.major, prop.minor);
     return W2VSEG_ERR_CUDA;
   }
+  cached_dev = dev;
   return 0;
 }
 

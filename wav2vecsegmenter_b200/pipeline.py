@@ -1,0 +1,252 @@
+"""Host logic of the SFC path around the CUDA forward: the window plan of a talk, the per-window
+metadata that reproduces the reference's batch-dependent behaviour, device batching, sharding of
+windows across ranks, and the talk-level reductions.
+
+Reference behaviour reproduced (all host-side integer logic, bit-exact):
+  * fixed-length tiling i of a talk                       lib/dataset.py:612-639
+  * sample -> frame indices (numpy round-half-even)       lib/dataset.py:604-606, 665-666
+  * CollateFn: `included`, padded length of the batch     lib/datautils.py:88, 98-103, 122-125
+  * the +-1 frame fix-up incl. `ends -= 1` for the batch  lib/evaluate.py:63-70
+  * scatter into the talk vector, NaN fill                lib/evaluate.py:100-125
+  * average over tilings                                  segment.py:101-108
+The reference batches `batch_size` CONSECUTIVE windows of one tiling; two things depend on that
+grouping (the normalisation length and the fix-up), so each window carries them as metadata and
+the device is free to batch / shard windows any other way.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+INPUT_SR = 16_000
+TARGET_SR = 49.95
+_CONV_K = (10, 3, 3, 3, 3, 2, 2)
+_CONV_S = (5, 2, 2, 2, 2, 2, 2)
+
+
+def num_frames(n: int) -> int:
+    """conv-stack output length (same arithmetic as w2vseg_num_frames / HF:1005-1024)"""
+    for k, s in zip(_CONV_K, _CONV_S):
+        if n < k:
+            return 0
+        n = (n - k) // s + 1
+    return int(n)
+
+
+def samples_to_frames(x) -> int:
+    return int(np.round(x * (1 / (INPUT_SR / TARGET_SR))).astype(int))
+
+
+@dataclass
+class Window:
+    talk: int            # talk index
+    tiling: int          # inference iteration i
+    start: int           # samples
+    end: int
+    start_f: int         # frames (output space)
+    end_f: int
+    norm_len: int = 0    # padded length of the reference batch (0 = silent window, not normalised)
+    out_len: int = 0     # leading true entries of the (possibly trimmed) out_mask row
+    ends_shift: int = 0  # 1 if the reference decrements `ends` for this window's batch
+    included: bool = True
+
+    @property
+    def n_samples(self) -> int:
+        return self.end - self.start
+
+
+def tiling_bounds(duration: int, segment_sec: float, inference_times: int, i: int):
+    seg = int(np.round(segment_sec * INPUT_SR).astype(int))
+    start = round(seg / inference_times * i)
+    if start > duration:
+        start = 0
+    cuts = np.arange(start, duration, seg).astype(int)
+    if cuts[0] != 0:
+        cuts = np.insert(cuts, 0, 0)
+    if cuts[-1] != duration:
+        if duration - cuts[-1] < int(np.round(2 * INPUT_SR).astype(int)):
+            cuts[-1] = duration
+        else:
+            cuts = np.append(cuts, duration)
+    return [int(c) for c in cuts[:-1]], [int(c) for c in cuts[1:]]
+
+
+def plan_tiling(duration: int, segment_sec: float, inference_times: int, i: int, batch_size: int,
+                talk: int = 0, included=None) -> list[Window]:
+    """windows of tiling i with the reference-batch metadata filled in. `included[k]` (optional)
+    = whether window k has a non-zero sample sum (lib/datautils.py:88)."""
+    starts, ends = tiling_bounds(duration, segment_sec, inference_times, i)
+    wins = [Window(talk, i, s, e, samples_to_frames(s + 1e-6), samples_to_frames(e + 1e-6))
+            for s, e in zip(starts, ends)]
+    if included is not None:
+        for w, inc in zip(wins, included):
+            w.included = bool(inc)
+    for b0 in range(0, len(wins), batch_size):
+        group = wins[b0: b0 + batch_size]
+        lmax = max(w.n_samples for w in group)
+        t_hidden = num_frames(lmax)
+        t_mask = max(w.end_f - w.start_f for w in group)
+        shift = 0
+        if t_hidden < t_mask:
+            if t_mask - t_hidden != 1:
+                raise ValueError("reference cannot run this batch: out_mask is more than one frame "
+                                 f"longer than the encoder output ({t_mask} vs {t_hidden})")
+            shift = 1
+        elif t_hidden - t_mask > 1:
+            raise ValueError("reference cannot run this batch: encoder output is more than one frame "
+                             f"longer than out_mask ({t_hidden} vs {t_mask})")
+        for w in group:
+            w.norm_len = lmax if w.included else 0
+            w.out_len = min(w.end_f - w.start_f, t_mask - shift)
+            w.ends_shift = shift
+    return wins
+
+
+def scatter_plan(wins: list[Window], n_frames: int):
+    """(start[], count[], nan_idx[]) for w2vseg_scatter_rows / w2vseg_nanfill: what
+    lib/evaluate.py:100-111 writes, in window order, and which frames stay NaN afterwards."""
+    start, count = [], []
+    covered = np.zeros(n_frames, dtype=bool)
+    for w in wins:
+        s, e = w.start_f, w.end_f - w.ends_shift
+        s_c, e_c = max(0, min(s, n_frames)), max(0, min(e, n_frames))
+        if w.included and e > s:
+            start.append(s)
+            count.append(e - s)
+            covered[s_c:e_c] = True
+        elif not w.included:
+            start.append(s)
+            count.append(-(e - s) if e > s else 0)
+            covered[s_c:e_c] = True
+        else:
+            start.append(s)
+            count.append(0)
+    return (np.asarray(start, dtype=np.int32), np.asarray(count, dtype=np.int32),
+            np.flatnonzero(~covered).astype(np.int32))
+
+
+def shard_ranges(n: int, world: int):
+    """contiguous, balanced shards: rank r owns [lo, hi)"""
+    base, rem = divmod(n, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+@dataclass
+class TalkResult:
+    probs: np.ndarray                 # averaged over tilings, float64 [n_frames]
+    per_tiling: list = field(default_factory=list)
+
+
+class TalkRunner:
+    """Runs whole talks through an SFCEngine. `device_batch` is the number of windows per forward
+    call (independent of the reference `batch_size`, which only shapes the metadata)."""
+
+    def __init__(self, engine, batch_size: int = 14, segment_sec: float = 20, inference_times: int = 1,
+                 device_batch: int | None = None, dist_group=None):
+        self.engine = engine
+        self.batch_size = int(batch_size)
+        self.segment_sec = segment_sec
+        self.inference_times = int(inference_times)
+        self.device_batch = int(device_batch or batch_size)
+        self.dist_group = dist_group
+
+    # -------------------------------------------------------------------------------------
+    def plan(self, waves: list[np.ndarray]) -> tuple[list[Window], list[int]]:
+        import torch
+
+        wins, n_frames = [], []
+        for t, wave in enumerate(waves):
+            dur = len(wave)
+            n_frames.append(samples_to_frames(dur))
+            wt = torch.from_numpy(np.ascontiguousarray(wave))
+            for i in range(self.inference_times):
+                s, e = tiling_bounds(dur, self.segment_sec, self.inference_times, i)
+                inc = [bool(wt[a:b].sum()) for a, b in zip(s, e)]  # lib/datautils.py:88
+                wins += plan_tiling(dur, self.segment_sec, self.inference_times, i, self.batch_size, t, inc)
+        return wins, n_frames
+
+    def _forward_rows(self, waves_dev, wins: list[Window], r_max: int):
+        """probability rows fp32 [len(wins), r_max] on the device for the given windows"""
+        import torch
+
+        eng = self.engine
+        rows = torch.zeros(len(wins), r_max, dtype=torch.float32, device=eng.device)
+        for b0 in range(0, len(wins), self.device_batch):
+            group = wins[b0: b0 + self.device_batch]
+            lmax = max(w.n_samples for w in group)
+            if lmax < 400:
+                continue  # shorter than one receptive field: no frames at all
+            stage = torch.zeros(len(group), lmax, dtype=torch.float32, device=eng.device)
+            for k, w in enumerate(group):
+                stage[k, : w.n_samples] = waves_dev[w.talk][w.start: w.end]
+            _, probs = eng.sfc_forward(stage, [w.n_samples for w in group], [w.norm_len for w in group],
+                                       [w.out_len for w in group], lmax)
+            R = probs.shape[1]
+            rows[b0: b0 + len(group), : min(R, r_max)] = probs[:, : min(R, r_max)]
+        return rows
+
+    def run(self, waves: list[np.ndarray]) -> list[TalkResult]:
+        """waves: one float32 array of raw samples per talk. Returns per-talk probabilities."""
+        import torch
+
+        eng = self.engine
+        wins, n_frames = self.plan(waves)
+        r_max = max([eng.frame_stride(max(w.n_samples, 400)) for w in wins] + [1])
+        world, rank = 1, 0
+        if self.dist_group is not None:
+            import torch.distributed as dist
+
+            world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
+        lo, hi = shard_ranges(len(wins), world)[rank]
+        waves_dev = {}
+        for w in wins[lo:hi]:
+            if w.talk not in waves_dev:
+                waves_dev[w.talk] = torch.from_numpy(np.ascontiguousarray(waves[w.talk], dtype=np.float32)).to(
+                    eng.device, non_blocking=True)
+        rows = self._forward_rows(waves_dev, wins[lo:hi], r_max)
+        if world > 1:
+            rows = gather_rows(rows, len(wins), world, self.dist_group)
+        return self.reduce(rows, wins, n_frames)
+
+    def reduce(self, rows, wins: list[Window], n_frames: list[int]) -> list[TalkResult]:
+        """rows [len(wins), r] (device) -> per-talk averaged probabilities (scatter, NaN fill,
+        tiling average on the device; one D2H per talk)"""
+        import torch
+
+        eng = self.engine
+        out = []
+        for t, n in enumerate(n_frames):
+            tilings = torch.empty(self.inference_times, n, dtype=torch.float64, device=eng.device)
+            for i in range(self.inference_times):
+                idx = [k for k, w in enumerate(wins) if w.talk == t and w.tiling == i]
+                sub = [wins[k] for k in idx]
+                st, ct, nan_idx = scatter_plan(sub, n)
+                talk_rows = rows[idx[0]: idx[-1] + 1] if idx else rows[:0]
+                talk = eng.scatter_rows(talk_rows, st, ct, n)
+                eng.nanfill(talk, nan_idx)
+                tilings[i] = talk
+            avg = eng.overlap_average(tilings)
+            out.append(TalkResult(avg.cpu().numpy(), [tilings[i].cpu().numpy() for i in range(self.inference_times)]))
+        return out
+
+
+def gather_rows(rows, n_total: int, world: int, group=None):
+    """NCCL (or gloo) all_gather of the per-rank probability rows — the only data that crosses
+    NVLink on this path. Shards are contiguous and balanced, so padding every rank to the largest
+    shard and trimming after the gather restores window order."""
+    import torch
+    import torch.distributed as dist
+
+    per = (n_total + world - 1) // world
+    pad = torch.zeros(per, rows.shape[1], dtype=rows.dtype, device=rows.device)
+    pad[: rows.shape[0]] = rows
+    buf = torch.empty(world * per, rows.shape[1], dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    parts = [buf[r * per: r * per + (hi - lo)] for r, (lo, hi) in enumerate(shard_ranges(n_total, world))]
+    return torch.cat(parts, dim=0)
