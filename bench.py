@@ -193,31 +193,31 @@ def run_native(args):
     audio_sec = world * BATCH * WIN_SEC * args.steps
     value = audio_sec / (ms / 1e3)
 
-    # ---- end to end through the public host API: pinned host audio -> H2D -> forward -> D2H probs
-    host_audio = [a.cpu().pin_memory() for a in audio[:2]]
-    host_probs = torch.empty(BATCH, R).pin_memory()
-    dev_in = [torch.empty(BATCH, WIN_SAMPLES, device=dev) for _ in range(2)]
-    lens_host = [WIN_SAMPLES] * BATCH
+    # ---- end to end through the public host API (the call a user makes): a 280 s talk held in
+    # pinned HOST memory -> TalkRunner.run(): window plan, H2D, fused forward, scatter / NaN fill /
+    # tiling average on the device, D2H of the per-frame probabilities. All inside the timed region.
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    runner = TalkRunner(eng, batch_size=BATCH, segment_sec=WIN_SEC, inference_times=1)
+    talks = [(torch.randn(BATCH * WIN_SAMPLES, generator=torch.Generator().manual_seed(7 + i)) * 0.1)
+             .pin_memory().numpy() for i in range(2)]
 
     def e2e_step(i):
-        # host -> device copy of this step's input, forward, device -> host read of its result
-        buf = dev_in[i % 2]
-        buf.copy_(host_audio[i % 2], non_blocking=True)
-        eng.sfc_forward(buf, lens, lens, out_len, WIN_SAMPLES, logits, probs)
-        host_probs.copy_(probs, non_blocking=True)
+        return runner.run([talks[i % 2]])[0].probs
 
     for i in range(max(2, args.warmup)):
         e2e_step(i)
     barrier()
     e0.record()
     for i in range(args.steps):
-        e2e_step(i)
+        out_probs = e2e_step(i)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = audio_sec / (float(t.item()) / 1e3)
+    e2e_d2h = int(out_probs.nbytes)
 
     # ---- per-kernel device timing (CUDA events around every launch, on the launching stream)
     roofline, kernels = None, None
@@ -239,21 +239,26 @@ def run_native(args):
         gemm_names = [k for k in kernels if k.startswith("gemm.") and k != "gemm.pos_conv"]
         gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_names)
         gemm_fl = sum(fl[k] for k in gemm_names) * BATCH
-        gemm_launches = sum(kernels[k]["launches_per_step"] for k in gemm_names)
-        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        step_ms = sum(k["ms_per_step"] for k in kernels.values())
+        dom = "gemm.ffn_up"   # the launch family with the largest share of the step
+        dom_ms, dom_n = kernels[dom]["ms_per_step"], kernels[dom]["launches_per_step"]
+        achieved = fl[dom] * BATCH / (dom_ms / 1e3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "gemm_traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get("kernels", {}).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {
-            "kernel": "gemm_tc_kernel<256> (tcgen05/TMEM/TMA; all Linear + conv layers 1-6)",
+            "kernel": "gemm_tc_kernel<256,0> FFN-up launches (M=13986 N=4608 K=1024, bias+GELU/ReLU, bf16 out; tcgen05/TMEM/TMA)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
             "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
             "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
             "traffic": traffic,
-            "launches_per_step": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
-            "algorithmic_gflop_per_step": round(gemm_fl / 1e9, 1),
-            "share_of_step": round(gemm_ms / sum(k["ms_per_step"] for k in kernels.values()), 4),
+            "launches_per_step": dom_n, "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
+            "algorithmic_gflop_per_launch": round(fl[dom] * BATCH / dom_n / 1e9, 1),
+            "share_of_step": round(dom_ms / step_ms, 4),
+            "all_gemm256": {"tflops": round(gemm_fl / (gemm_ms / 1e3) / 1e12, 1),
+                            "frac": round(gemm_fl / (gemm_ms / 1e3) / 1e12 / peaks["tflops_sustained"], 4),
+                            "share_of_step": round(gemm_ms / step_ms, 4)},
             "whole_path_frac": round(value / world * (total_fl / WIN_SEC) / 1e12 / peaks["tflops_sustained"], 4),
         }
         for k, v in kernels.items():
@@ -275,7 +280,8 @@ def run_native(args):
                        "l2": "inputs rotate over 4 batches; per-step working set ~2.1 GB >> 126 MB L2",
                        "weights": "random-init, seed 0"},
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s",
-                    "h2d_bytes_per_step": BATCH * WIN_SAMPLES * 4, "d2h_bytes_per_step": BATCH * R * 4},
+                    "h2d_bytes_per_step": BATCH * WIN_SAMPLES * 4, "d2h_bytes_per_step": e2e_d2h,
+                    "api": "wav2vecsegmenter_b200.pipeline.TalkRunner.run (host wave in, per-frame probabilities out)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
