@@ -195,6 +195,11 @@ int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C
 int32_t w2vseg_attention(const void* qkv_bf16, int32_t B, int32_t R, int32_t heads,
                          int32_t head_dim, const int32_t* kv_len, float scale, void* ctx_bf16,
                          void* stream);
+/* same contract on the legacy warp-level mma.sync path: kept as an independent second
+ * implementation for the parity tests of the tcgen05 kernel, not used by the forward pass */
+int32_t w2vseg_attention_mma(const void* qkv_bf16, int32_t B, int32_t R, int32_t heads,
+                             int32_t head_dim, const int32_t* kv_len, float scale, void* ctx_bf16,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -129,20 +129,24 @@ def test_layernorm(lib, C, in_f32, act):
     assert (out.float() - ref).abs().mean().item() < 3e-3
 
 
+@pytest.mark.parametrize("impl", ["w2vseg_attention", "w2vseg_attention_mma"])
 @pytest.mark.parametrize("heads,dh", [(16, 64), (8, 128)])
-@pytest.mark.parametrize("R,lens", [(1000, [999, 999]), (333, [333, 1, 200]), (130, [64, 65, 0, 130])])
-def test_attention(lib, heads, dh, R, lens):
+@pytest.mark.parametrize("R,lens", [(1000, [999, 999]), (333, [333, 1, 200]), (130, [64, 65, 0, 130]),
+                                    (1100, [1099, 128, 129, 257])])
+def test_attention(lib, heads, dh, R, lens, impl):
     from wav2vecsegmenter_b200 import _native as n
 
     B = len(lens)
     D = heads * dh
     g = torch.Generator(device="cuda").manual_seed(R + dh)
-    qkv = torch.randn(B * R, 3 * D, device="cuda", generator=g).bfloat16()
+    qkv = torch.randn(B * R, 3 * D, device="cuda", generator=g)
+    qkv[:, :D] *= 3.0  # sharper softmax: running-max updates (and the lazy O rescale) get exercised
+    qkv = qkv.bfloat16()
     kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32)
     ctx = torch.empty(B * R, D, device="cuda", dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(dh)
-    n.check(lib.w2vseg_attention(n.ptr(qkv), B, R, heads, dh, n.ptr(kv_len), scale, n.ptr(ctx),
-                                 n.current_stream_ptr()))
+    n.check(getattr(lib, impl)(n.ptr(qkv), B, R, heads, dh, n.ptr(kv_len), scale, n.ptr(ctx),
+                               n.current_stream_ptr()))
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(B, R, 3, heads, dh).permute(2, 0, 3, 1, 4)  # [B, H, R, dh]
     s = (q @ k.transpose(-1, -2)) * scale

@@ -347,7 +347,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       prof_tag("gemm.qkv");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
-    W2V_TRY(attention_launch(w.qkv, B, R, c.heads, h->DH, w.enc_len, 1.0f / sqrtf((float)h->DH),
+    W2V_TRY(attention_tc_launch(w.qkv, B, R, c.heads, h->DH, w.enc_len, 1.0f / sqrtf((float)h->DH),
                              w.ctx, st));
     {
       GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
@@ -389,7 +389,7 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc_launch(g, 256, st));
     }
-    W2V_TRY(attention_launch(w.qkv, B, R, c.head_heads, hd, out_len, 1.0f / sqrtf((float)hd), w.ctx, st));
+    W2V_TRY(attention_tc_launch(w.qkv, B, R, c.head_heads, hd, out_len, 1.0f / sqrtf((float)hd), w.ctx, st));
     {
       GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
@@ -649,6 +649,14 @@ int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C
 
 int32_t w2vseg_attention(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
                          const int32_t* kv_len, float scale, void* ctx, void* stream) {
+  W2V_REQUIRE(qkv && kv_len && ctx, "attention: null argument");
+  W2V_TRY(w2vseg_device_ok());
+  return attention_tc_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
+                             (cudaStream_t)stream);
+}
+
+int32_t w2vseg_attention_mma(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                             const int32_t* kv_len, float scale, void* ctx, void* stream) {
   W2V_REQUIRE(qkv && kv_len && ctx, "attention: null argument");
   return attention_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
                           (cudaStream_t)stream);

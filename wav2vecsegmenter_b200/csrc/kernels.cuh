@@ -42,6 +42,10 @@ int head_final_launch(const float* y, int B, int R, int C, const float* gamma, c
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
                      const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s);
 
+// same contract, tcgen05 / TMEM / TMA implementation (attention_tc.cu) — the product path
+int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
+                        const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s);
+
 // ---- weight packing -----------------------------------------------------------------------
 // dst_bf16[r*ld_dst + c] = src[r*cols + c] * scale
 int pack_matrix_launch(const float* src, int rows, int cols, float scale, __nv_bfloat16* dst,
