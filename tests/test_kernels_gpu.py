@@ -58,6 +58,8 @@ def _ref_act(x, act):
     ],
 )
 def test_gemm(lib, M, N, K, act, out_f32, use_resid, block_n):
+    if block_n == 64 and not out_f32:
+        pytest.skip("bf16 output is only built for block_n >= 128")
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + act)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()

@@ -58,6 +58,12 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -211,27 +217,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int hea
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
-      float s[AT_BN];
+      // ---- pass 1: row max. All four 32-column loads are issued before the single wait; the
+      // values are dropped again (S stays in TMEM), which keeps the kernel inside the 168-register
+      // budget of two CTAs per SM without spilling.
+      float mx;
+      {
+        uint32_t raw[4][32];
 #pragma unroll
-      for (int c = 0; c < AT_BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), raw);
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), raw[c]);
         tc_wait_ld();
+        const int kbase = j * AT_BN;
+        float m8[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]) * scale_log2;
+        for (int i = 0; i < 8; ++i) m8[i] = -INFINITY;
+        if (kbase + AT_BN > klen) {                  // only the last tile has masked keys
+#pragma unroll
+          for (int i = 0; i < AT_BN; ++i) {
+            const float v = (kbase + i < klen) ? __uint_as_float(raw[i >> 5][i & 31]) : -INFINITY;
+            m8[i & 7] = fmaxf(m8[i & 7], v);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < AT_BN; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(raw[i >> 5][i & 31]));
+        }
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                   fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * scale_log2;
       }
-      tc_fence_before();
-      mbar_arrive(s_free);                           // S may be overwritten by QK^T of tile j+1
-
-      const int kbase = j * AT_BN;
-      if (kbase + AT_BN > klen) {                    // only the last tile has masked keys
-#pragma unroll
-        for (int i = 0; i < AT_BN; ++i)
-          if (kbase + i >= klen) s[i] = -INFINITY;
-      }
-      float mx = s[0];
-#pragma unroll
-      for (int i = 1; i < AT_BN; ++i) mx = fmaxf(mx, s[i]);
 
       float factor = 1.f;
       bool need = false;
@@ -240,7 +251,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int hea
       } else {
         need = mx > m_used + AT_RESCALE_THRESHOLD;
         if (need) {
-          factor = exp2f(m_used - mx);
+          factor = ex2_approx(m_used - mx);
           m_used = mx;
           l_sum *= factor;
         }
@@ -261,27 +272,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int hea
         }
       }
 
-      // P row: exp2, running sum, bf16, 16-byte chunks into the K-major SW128 layout
-      float sum = 0.f;
+      // ---- pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per element), 4 partial sums, bf16,
+      // 16-byte chunks into the K-major SW128 layout; the load of chunk c+1 is in flight while
+      // chunk c is processed. Masked keys get p = 0 exactly.
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m_used;
+      const int n_valid = klen - j * AT_BN;          // >= 1; >= 128 except for the last tile
+      uint32_t rb[2][32];
+      tmem_ld_32x32b_x32(tS + lane_off, rb[0]);
 #pragma unroll
-      for (int ch = 0; ch < AT_BN / 8; ++ch) {
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = exp2f(s[ch * 8 + i] - m_used);
-          sum += p[i];
+      for (int c = 0; c < 4; ++c) {
+        tc_wait_ld();
+        if (c + 1 < 4) {
+          tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)((c + 1) * 32), rb[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          mbar_arrive(s_free);                       // S may be overwritten by QK^T of tile j+1
         }
-        uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]);
-        u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]);
-        u.w = pack_bf16x2(p[6], p[7]);
-        const uint32_t addr = smem_u32(sP) + (uint32_t)((ch >> 3) * (AT_BM * 128) + r * 128 +
-                                                        (((ch & 7) ^ (r & 7)) << 4));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y),
-                     "r"(u.z), "r"(u.w)
-                     : "memory");
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = c * 32 + g * 8 + i;
+            const float e = ex2_approx(fmaf(__uint_as_float(rb[c & 1][g * 8 + i]), scale_log2, neg_m));
+            p[i] = (col < n_valid) ? e : 0.f;
+            sum4[i & 3] += p[i];
+          }
+          uint4 u;
+          u.x = pack_bf16x2(p[0], p[1]);
+          u.y = pack_bf16x2(p[2], p[3]);
+          u.z = pack_bf16x2(p[4], p[5]);
+          u.w = pack_bf16x2(p[6], p[7]);
+          const int ch = c * 4 + g;
+          const uint32_t addr = smem_u32(sP) + (uint32_t)((ch >> 3) * (AT_BM * 128) + r * 128 +
+                                                          (((ch & 7) ^ (r & 7)) << 4));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y),
+                       "r"(u.z), "r"(u.w)
+                       : "memory");
+        }
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l_sum += sum;
       fence_proxy_async_smem();                      // generic-proxy stores -> visible to the MMA
       tc_fence_before();

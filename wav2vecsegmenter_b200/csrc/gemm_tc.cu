@@ -26,7 +26,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 256:4, 128:6, 64:8
   static constexpr int TMEM_COLS = 2 * BLOCK_N;               // 512 / 256 / 128 (powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
 struct KernelArgs {
@@ -150,13 +151,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     // 8 warps: warp w reads TMEM lane quarter (w & 3) — the only one it may touch — and the
-    // column half (w - 2) >> 2 of the tile. Thread = one accumulator row, 32 columns per step;
-    // the tcgen05.ld (and the residual read) of step c+1 is in flight while step c is processed.
+    // column half (w - 2) >> 2 of the tile. TMEM hands each thread one accumulator ROW; written
+    // to global memory that way every warp store would touch 32 different cache lines. So each
+    // 32-row x 128-byte block is transposed through a per-warp, XOR-swizzled 4 KB staging buffer:
+    // bias / activation / row mask are applied row-per-thread, then the block is re-read with
+    // lane -> (row = k*4 + lane/8, 16-byte chunk = lane%8) so that every global load (residual)
+    // and store covers 4 full 128-byte lines. TMEM loads run one step ahead of the math.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int COLS = BLOCK_N / 2;       // columns per warp
-    constexpr int NCHUNK = COLS / 32;
-    const int r_in_tile = q * 32 + lane;
+    constexpr int COLS = BLOCK_N / 2;                 // columns per warp
+    constexpr int UNIT = OUT_F32 ? 32 : 64;           // columns per staging block (128 B per row)
+    static_assert(COLS % UNIT == 0, "bf16 output needs BLOCK_N >= 128");
+    constexpr int NUNIT = COLS / UNIT;
+    constexpr int LPU = UNIT / 32;                    // tcgen05.ld x32 per unit
+    const uint32_t stage = smem_u32(smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * 4096);
+    const int c_row = lane >> 3;                      // coalesced phase: row within a group of 4
+    const int c_chk = lane & 7;                       //                  16-byte chunk of the row
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -164,95 +174,127 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int mt = tile / n_tiles;
       const int g = mt / p.tiles_m_per_group;
       const int i = mt - g * p.tiles_m_per_group;
-      const int r_in_group = i * BLOCK_M + r_in_tile;
-      const bool row_ok = r_in_group < p.rows_per_group;
-      const long long orow = (long long)g * p.o_group_rows + r_in_group;
-      bool zero_row = false;
-      if (p.mask_len != nullptr && row_ok) {
+      const int rg0 = i * BLOCK_M + q * 32;           // first row (in group) of this warp's block
+      const long long orow0 = (long long)g * p.o_group_rows + rg0;
+      bool zero_row = false;                          // row-per-thread view: row rg0 + lane
+      if (p.mask_len != nullptr && rg0 + lane < p.rows_per_group) {
+        const long long orow = orow0 + lane;
         const long long w = orow / p.mask_period;
-        const int t = (int)(orow - w * p.mask_period);
-        zero_row = t >= __ldg(p.mask_len + w);
+        zero_row = (int)(orow - w * p.mask_period) >= __ldg(p.mask_len + w);
       }
       const int colbase = nb * BLOCK_N + half * COLS;
-      const bool use_resid = OUT_F32 && p.resid != nullptr && row_ok;
-      const float4* r4 = use_resid
-          ? reinterpret_cast<const float4*>(p.resid + orow * p.ld_resid + colbase) : nullptr;
+      const bool use_resid = OUT_F32 && p.resid != nullptr;
 
       float4 res[2][8];
-      if (OUT_F32 && use_resid) {
+      if constexpr (OUT_F32) {
+        if (use_resid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) res[0][j] = r4[j];
+          for (int k = 0; k < 8; ++k) {
+            const int rr = k * 4 + c_row;
+            if (rg0 + rr < p.rows_per_group)
+              res[0][k] = *reinterpret_cast<const float4*>(p.resid + (orow0 + rr) * p.ld_resid +
+                                                           colbase + c_chk * 4);
+          }
+        }
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)(acc * BLOCK_N + half * COLS);
-      uint32_t raw[2][32];
-      tmem_ld_32x32b_x32(t_base, raw[0]);
+      uint32_t raw[UNIT];
+#pragma unroll
+      for (int l = 0; l < LPU; ++l)
+        tmem_ld_32x32b_x32(t_base + (uint32_t)(l * 32), *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
 
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int u = 0; u < NUNIT; ++u) {
         tc_wait_ld();
-        if (c + 1 < NCHUNK) {
-          tmem_ld_32x32b_x32(t_base + (uint32_t)((c + 1) * 32), raw[(c + 1) & 1]);
-          if (OUT_F32 && use_resid) {
+        if (u + 1 < NUNIT) {
+          if constexpr (OUT_F32) {
+            if (use_resid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) res[(c + 1) & 1][j] = r4[(c + 1) * 8 + j];
+              for (int k = 0; k < 8; ++k) {
+                const int rr = k * 4 + c_row;
+                if (rg0 + rr < p.rows_per_group)
+                  res[(u + 1) & 1][k] = *reinterpret_cast<const float4*>(
+                      p.resid + (orow0 + rr) * p.ld_resid + colbase + (u + 1) * UNIT + c_chk * 4);
+              }
+            }
           }
         }
-        const int col0 = colbase + c * 32;
+        const int col0 = colbase + u * UNIT;
         const int act = (col0 < p.act_split) ? p.act_lo : p.act_hi;
-        float v[32];
+        float v[UNIT];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+        for (int j = 0; j < UNIT; ++j) v[j] = __uint_as_float(raw[j]);
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < UNIT / 4; ++j) {
             const float4 b = __ldg(b4 + j);
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
         if (act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < UNIT; ++j) v[j] = gelu_erf(v[j]);
         } else if (act == ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < UNIT; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (zero_row) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int j = 0; j < UNIT; ++j) v[j] = 0.f;
         }
-        if (row_ok) {
+        // row-per-thread -> staging (row = lane, 8 chunks of 16 B, chunk index XOR row%8)
+        const uint32_t srow = stage + (uint32_t)(lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t w0, w1, w2, w3;
           if constexpr (OUT_F32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                   orow * p.ld_out + col0);
-            if (use_resid) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = res[c & 1][j];
-                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            w0 = __float_as_uint(v[4 * j + 0]); w1 = __float_as_uint(v[4 * j + 1]);
+            w2 = __float_as_uint(v[4 * j + 2]); w3 = __float_as_uint(v[4 * j + 3]);
           } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                 orow * p.ld_out + col0);
+            w0 = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); w1 = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            w2 = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); w3 = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((j ^ (lane & 7)) << 4)),
+                       "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                       : "memory");
+        }
+        if (u + 1 < NUNIT) {   // accumulator registers are free again: fetch the next block now,
+#pragma unroll               // its latency hides behind the store phase below
+          for (int l = 0; l < LPU; ++l)
+            tmem_ld_32x32b_x32(t_base + (uint32_t)((u + 1) * UNIT + l * 32),
+                               *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
+        }
+        __syncwarp();
+        // staging -> global, coalesced: 4 rows x 128 B per warp instruction
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              o4[j] = u;
+        for (int k = 0; k < 8; ++k) {
+          const int rr = k * 4 + c_row;
+          uint4 x;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                       : "r"(stage + (uint32_t)(rr * 128 + ((c_chk ^ (rr & 7)) << 4))));
+          if (rg0 + rr < p.rows_per_group) {
+            if constexpr (OUT_F32) {
+              float4 f = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z),
+                                     __uint_as_float(x.w));
+              if (use_resid) {
+                const float4 rv = res[u & 1][k];
+                f.x += rv.x; f.y += rv.y; f.z += rv.z; f.w += rv.w;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ld_out + col0 +
+                                         c_chk * 4) = f;
+            } else {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ld_out +
+                                        col0 + c_chk * 8) = x;
             }
           }
         }
+        __syncwarp();
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back
       tc_fence_before();
@@ -298,9 +340,11 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
     W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
+    if constexpr (BLOCK_N >= 128) {
+      W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES));
+    }
     attr_set = true;
   }
   const long long num_tiles =
@@ -309,10 +353,12 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
   const int grid = (int)(num_tiles < (long long)num_sms() ? num_tiles : (long long)num_sms());
   {
     ProfScope ps(stream, BLOCK_N == 256 ? "gemm_bn256" : (BLOCK_N == 128 ? "gemm_bn128" : "gemm_bn64"));
-    if (g.out_f32)
+    if (g.out_f32) {
       gemm_tc_kernel<BLOCK_N, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
-    else
-      gemm_tc_kernel<BLOCK_N, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+    } else {
+      if constexpr (BLOCK_N >= 128)
+        gemm_tc_kernel<BLOCK_N, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+    }
   }
   W2V_CHECK_LAUNCH();
   return 0;
@@ -329,6 +375,7 @@ int gemm_tc_launch(const GemmProblem& g, int block_n, cudaStream_t stream) {
               "gemm: output/residual leading dimensions must keep 16-byte alignment");
   W2V_REQUIRE(g.resid == nullptr || g.out_f32, "gemm: residual requires fp32 output");
   W2V_REQUIRE(g.a_row_stride % 8 == 0, "gemm: A row stride must be a multiple of 8 elements");
+  W2V_REQUIRE(g.out_f32 || block_n >= 128, "gemm: bf16 output needs block_n >= 128");
   switch (block_n) {
     case 256: return launch_impl<256>(g, stream);
     case 128: return launch_impl<128>(g, stream);
