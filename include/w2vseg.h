@@ -177,7 +177,8 @@ int32_t w2vseg_moving_average(const double* arr, int64_t n, int32_t window, doub
 
 /* ---- single kernels (unit tests, ncu) ------------------------------------------------------- */
 /* out = epilogue(A[M,K] * W[N,K]^T): bf16 operands, fp32 accumulate on tcgen05.
- * act: 0 none, 1 erf-GELU, 2 ReLU. resid (fp32 [M,N]) requires out_f32 = 1. block_n 64/128/256. */
+ * act: 0 none, 1 erf-GELU, 2 ReLU. resid (fp32 [M,N]) requires out_f32 = 1. block_n 64/128/256
+ * selects the single-CTA tile width; block_n 512 selects the CTA-pair (cta_group::2) 256x256 kernel. */
 int32_t w2vseg_gemm(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N, int32_t K,
                     const float* bias, int32_t act, const float* resid, void* out,
                     int32_t out_f32, int32_t block_n, void* stream);

@@ -13,6 +13,7 @@ lib = n.load()
 M = 14000
 shapes = [("ffn_up", 4608, 1024, 1, 0), ("ffn_down", 1024, 4608, 0, 1), ("qkv", 3072, 1024, 0, 0)]
 g = torch.Generator(device="cuda").manual_seed(0)
+BN = int(os.environ.get("BLOCK_N", "256"))
 for name, N, K, act, f32 in shapes:
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) / 32).bfloat16()
@@ -22,12 +23,12 @@ for name, N, K, act, f32 in shapes:
     NW, NT = (1, 1) if os.environ.get('NCU') else (3, 10)
     for _ in range(NW):
         n.check(lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out),
-                                f32, 256, n.current_stream_ptr()))
+                                f32, BN, n.current_stream_ptr()))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(NT):
-        lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out), f32, 256,
+        lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out), f32, BN,
                         n.current_stream_ptr())
     e1.record()
     torch.cuda.synchronize()

@@ -43,7 +43,7 @@ def _ref_act(x, act):
     return x
 
 
-@pytest.mark.parametrize("block_n", [256, 128, 64])
+@pytest.mark.parametrize("block_n", [512, 256, 128, 64])
 @pytest.mark.parametrize(
     "M,N,K,act,out_f32,use_resid",
     [

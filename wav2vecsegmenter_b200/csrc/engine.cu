@@ -628,6 +628,7 @@ int32_t w2vseg_gemm(const void* A, const void* W, int32_t M, int32_t N, int32_t 
   GemmProblem g = linear((const bf16*)A, M, K, (const bf16*)W, N, bias);
   g.act_lo = act; g.act_hi = act;
   g.resid = resid; g.ld_resid = N; g.out = out; g.ld_out = N; g.out_f32 = out_f32;
+  if (block_n == 512) return gemm_tc2_launch(g, (cudaStream_t)stream);  // CTA-pair 256x256 tiles
   return gemm_tc_launch(g, block_n, (cudaStream_t)stream);
 }
 

@@ -7,8 +7,7 @@
 //                                 accumulator row): tcgen05.ld -> bias/act/residual -> global.
 //                                 TMEM holds TWO accumulators so the epilogue of tile i overlaps
 //                                 the MMAs of tile i+1.
-#include "gemm_tc.cuh"
-#include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace w2v {
 
@@ -30,21 +29,6 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
-struct KernelArgs {
-  int N, K;
-  int num_groups, rows_per_group, tiles_m_per_group;
-  long long a_group_rows, o_group_rows;
-  int a_mode;
-  const float* bias;
-  int act_split, act_lo, act_hi;
-  const float* resid;
-  long long ld_resid;
-  void* out;
-  long long ld_out;
-  int out_f32;
-  const int* mask_len;
-  int mask_period;
-};
 
 template <int BLOCK_N, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -160,13 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int COLS = BLOCK_N / 2;                 // columns per warp
-    constexpr int UNIT = OUT_F32 ? 32 : 64;           // columns per staging block (128 B per row)
-    static_assert(COLS % UNIT == 0, "bf16 output needs BLOCK_N >= 128");
-    constexpr int NUNIT = COLS / UNIT;
-    constexpr int LPU = UNIT / 32;                    // tcgen05.ld x32 per unit
     const uint32_t stage = smem_u32(smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * 4096);
-    const int c_row = lane >> 3;                      // coalesced phase: row within a group of 4
-    const int c_chk = lane & 7;                       //                  16-byte chunk of the row
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -176,126 +154,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int i = mt - g * p.tiles_m_per_group;
       const int rg0 = i * BLOCK_M + q * 32;           // first row (in group) of this warp's block
       const long long orow0 = (long long)g * p.o_group_rows + rg0;
-      bool zero_row = false;                          // row-per-thread view: row rg0 + lane
-      if (p.mask_len != nullptr && rg0 + lane < p.rows_per_group) {
-        const long long orow = orow0 + lane;
-        const long long w = orow / p.mask_period;
-        zero_row = (int)(orow - w * p.mask_period) >= __ldg(p.mask_len + w);
-      }
-      const int colbase = nb * BLOCK_N + half * COLS;
-      const bool use_resid = OUT_F32 && p.resid != nullptr;
-
-      float4 res[2][8];
-      if constexpr (OUT_F32) {
-        if (use_resid) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rr = k * 4 + c_row;
-            if (rg0 + rr < p.rows_per_group)
-              res[0][k] = *reinterpret_cast<const float4*>(p.resid + (orow0 + rr) * p.ld_resid +
-                                                           colbase + c_chk * 4);
-          }
-        }
-      }
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)(acc * BLOCK_N + half * COLS);
-      uint32_t raw[UNIT];
-#pragma unroll
-      for (int l = 0; l < LPU; ++l)
-        tmem_ld_32x32b_x32(t_base + (uint32_t)(l * 32), *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
-
-#pragma unroll
-      for (int u = 0; u < NUNIT; ++u) {
-        tc_wait_ld();
-        if (u + 1 < NUNIT) {
-          if constexpr (OUT_F32) {
-            if (use_resid) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int rr = k * 4 + c_row;
-                if (rg0 + rr < p.rows_per_group)
-                  res[(u + 1) & 1][k] = *reinterpret_cast<const float4*>(
-                      p.resid + (orow0 + rr) * p.ld_resid + colbase + (u + 1) * UNIT + c_chk * 4);
-              }
-            }
-          }
-        }
-        const int col0 = colbase + u * UNIT;
-        const int act = (col0 < p.act_split) ? p.act_lo : p.act_hi;
-        float v[UNIT];
-#pragma unroll
-        for (int j = 0; j < UNIT; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-          for (int j = 0; j < UNIT / 4; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < UNIT; ++j) v[j] = gelu_erf(v[j]);
-        } else if (act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < UNIT; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (zero_row) {
-#pragma unroll
-          for (int j = 0; j < UNIT; ++j) v[j] = 0.f;
-        }
-        // row-per-thread -> staging (row = lane, 8 chunks of 16 B, chunk index XOR row%8)
-        const uint32_t srow = stage + (uint32_t)(lane * 128);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t w0, w1, w2, w3;
-          if constexpr (OUT_F32) {
-            w0 = __float_as_uint(v[4 * j + 0]); w1 = __float_as_uint(v[4 * j + 1]);
-            w2 = __float_as_uint(v[4 * j + 2]); w3 = __float_as_uint(v[4 * j + 3]);
-          } else {
-            w0 = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); w1 = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            w2 = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); w3 = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)((j ^ (lane & 7)) << 4)),
-                       "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                       : "memory");
-        }
-        if (u + 1 < NUNIT) {   // accumulator registers are free again: fetch the next block now,
-#pragma unroll               // its latency hides behind the store phase below
-          for (int l = 0; l < LPU; ++l)
-            tmem_ld_32x32b_x32(t_base + (uint32_t)((u + 1) * UNIT + l * 32),
-                               *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
-        }
-        __syncwarp();
-        // staging -> global, coalesced: 4 rows x 128 B per warp instruction
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int rr = k * 4 + c_row;
-          uint4 x;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                       : "r"(stage + (uint32_t)(rr * 128 + ((c_chk ^ (rr & 7)) << 4))));
-          if (rg0 + rr < p.rows_per_group) {
-            if constexpr (OUT_F32) {
-              float4 f = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z),
-                                     __uint_as_float(x.w));
-              if (use_resid) {
-                const float4 rv = res[u & 1][k];
-                f.x += rv.x; f.y += rv.y; f.z += rv.z; f.w += rv.w;
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ld_out + col0 +
-                                         c_chk * 4) = f;
-            } else {
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ld_out +
-                                        col0 + c_chk * 8) = x;
-            }
-          }
-        }
-        __syncwarp();
-      }
+      gemm_epilogue_warp<COLS, OUT_F32>(p, rg0, orow0, nb * BLOCK_N + half * COLS, t_base, stage, lane,
+                                        [&] {
+                                          mbar_wait(&tfull_bar[acc], acc_phase);
+                                          tc_fence_after();
+                                        });
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back
       tc_fence_before();
       __syncwarp();

@@ -52,4 +52,7 @@ struct GemmProblem {
 // Launches on `stream`. block_n in {64, 128, 256}; N % block_n == 0; K % 64 == 0.
 int gemm_tc_launch(const GemmProblem& p, int block_n, cudaStream_t stream);
 
+// CTA-pair (cta_group::2) 256x256-tile variant: a_mode 0, N % 256 == 0 (gemm_tc2.cu).
+int gemm_tc2_launch(const GemmProblem& p, cudaStream_t stream);
+
 }  // namespace w2v
