@@ -303,7 +303,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
     g.out = w.conv[l]; g.ld_out = CD;
     prof_tag(kConvK[l] == 3 ? "gemm.conv_k3" : "gemm.conv_k2");
-    W2V_TRY(gemm_tc_launch(g, 256, st));
+    W2V_TRY(gemm_tc2_launch(g, st));
     prof_tag("ln_gelu.conv");
     W2V_TRY(layernorm_launch(w.conv[l], false, rows_out, CD, h->conv_ln[l].g, h->conv_ln[l].b,
                              c.ln_eps, /*gelu*/ 1, w.conv[l], st));
@@ -316,7 +316,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     g.out = w.h; g.ld_out = D; g.out_f32 = 1;
     g.mask_len = w.enc_len; g.mask_period = R;
     prof_tag("gemm.feat_proj");
-    W2V_TRY(gemm_tc_launch(g, 256, st));
+    W2V_TRY(gemm_tc2_launch(g, st));
   }
 
   // positional conv embedding (HF:360-368) + residual (HF:764-765)
@@ -345,7 +345,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
       g.out = w.qkv; g.ld_out = 3 * D;
       prof_tag("gemm.qkv");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     W2V_TRY(attention_tc_launch(w.qkv, B, R, c.heads, h->DH, w.enc_len, 1.0f / sqrtf((float)h->DH),
                              w.ctx, st));
@@ -353,7 +353,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
       prof_tag("gemm.attn_out");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln2.g, L.ln2.b, c.ln_eps, 0, w.xn, st));
     {
@@ -361,13 +361,13 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
       g.out = w.mid; g.ld_out = L.F1;
       prof_tag("gemm.ffn_up");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, L.F1, L.w2, D, L.b2);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
       prof_tag("gemm.ffn_down");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
   }
   return 0;
@@ -387,14 +387,14 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       GemmProblem g = linear(w.xn, M, D, H.win, 3 * D, H.bin);
       g.out = w.qkv; g.ld_out = 3 * D;
       prof_tag("gemm.head");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     W2V_TRY(attention_tc_launch(w.qkv, B, R, c.head_heads, hd, out_len, 1.0f / sqrtf((float)hd), w.ctx, st));
     {
       GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
       prof_tag("gemm.head");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     W2V_TRY(layernorm_launch(y, true, M, D, H.ln2.g, H.ln2.b, c.ln_eps, 0, w.xn, st));
     {
@@ -402,13 +402,13 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
       g.out = w.mid; g.ld_out = c.head_ffn;
       prof_tag("gemm.head");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, c.head_ffn, H.w2, D, H.b2);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
       prof_tag("gemm.head");
-      W2V_TRY(gemm_tc_launch(g, 256, st));
+      W2V_TRY(gemm_tc2_launch(g, st));
     }
   }
   W2V_TRY(head_final_launch(y, B, R, D, h->head.lnf.g, h->head.lnf.b, c.ln_eps, h->head.wout,

@@ -208,7 +208,7 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   const long long max_clusters = num_sms() / 2;
   const int grid = 2 * (int)(num_tiles < max_clusters ? num_tiles : max_clusters);
   {
-    ProfScope ps(stream, "gemm2_256x256");
+    ProfScope ps(stream, "gemm_pair256");
     if (g.out_f32)
       gemm_tc2_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, a);
     else
