@@ -230,3 +230,42 @@ def test_segment_cli_generate(tmp_path):
     assert len(content) > 0 and set(content[0]) == {"duration", "offset", "rW", "uW", "speaker_id", "wav"}
     text = yaml.dump(content, default_flow_style=True)
     assert text.startswith("[{duration:")
+
+
+def test_long_form_two_hours(tiny_engine, seg):
+    """BASELINE.json configs[4]: one 2 h stream (115.2 M samples -> 360 windows, 359 640 frames)
+    through the whole-talk path; checked through size-independent properties + spot windows
+    against the oracle (the oracle itself needs ~1 s per window on CPU)."""
+    from oracle import sfc_oracle
+    from wav2vecsegmenter_b200.pipeline import TalkRunner, plan_tiling
+
+    n = 7200 * 16000
+    g = torch.Generator().manual_seed(11)
+    wave_t = torch.randn(n, generator=g) * (0.05 + 0.2 * torch.rand(n // 16000 + 1, generator=g).repeat_interleave(16000)[:n])
+    wave_f = wave_t.numpy()
+    res = TalkRunner(tiny_engine, batch_size=14, inference_times=1, device_batch=28).run([wave_f])[0]
+    assert len(res.probs) == 359_640 and np.isfinite(res.probs).all()
+    assert (res.probs >= 0).all() and (res.probs <= 1).all()
+    # spot-check three windows (first, a middle one, the last) against the CPU oracle
+    wins = plan_tiling(n, 20, 1, 0, 14)
+    assert len(wins) == 360
+    sd = synth.random_state_dict(synth.TINY, 0)
+    for k in (0, 173, 359):
+        w = wins[k]
+        x = wave_t[w.start: w.end][None]
+        xn = sfc_oracle.normalize_rows(x, [True])
+        mask = torch.ones(1, w.end_f - w.start_f, dtype=torch.bool)
+        with torch.no_grad():
+            p, _, m, _ = sfc_oracle.batch_probs(sd, xn, [w.n_samples], mask, synth.TINY.keep_layers, 8)
+        got = res.probs[w.start_f: w.start_f + m.shape[1]]
+        assert np.abs(got - p[0].numpy()).max() <= PROB_TOL
+    # all three algorithms run on the 2 h vector and produce well-formed, ordered, in-range records
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+        segs = fn(res.probs, **ALGOS[tag])
+        recs = seg.update_yaml_content([], segs, "long.wav")
+        assert len(recs) > 10
+        offs = [r["offset"] for r in recs]
+        assert offs == sorted(offs) and offs[0] >= 0 and offs[-1] + recs[-1]["duration"] <= 7200.1
+        if tag != "pthr":
+            assert max(r["duration"] for r in recs) <= ALGOS[tag]["max_segment_length"] + 0.2 or tag == "dac"
+        yaml.dump(recs, default_flow_style=True)
