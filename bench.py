@@ -123,8 +123,6 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep the version banner off stdout: ONE JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
@@ -139,6 +137,11 @@ def run_native(args):
     from wav2vecsegmenter_b200 import synth
     from wav2vecsegmenter_b200.engine import SFCEngine
 
+    # NCCL prints its version banner on stdout when the first communicator is created; the
+    # contract is ONE JSON line on stdout, so stdout is pointed at stderr until warm-up is over.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     world, rank, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -172,6 +175,9 @@ def run_native(args):
     for i in range(args.warmup):
         step(i)
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
