@@ -114,9 +114,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint64_t a_desc = make_desc_k_sw128(smem_u32(smem_a + stage * A_BYTES));
-            const uint64_t b_desc = make_desc_k_sw128(smem_u32(smem_b + stage * B_BYTES));
+          // descriptors are warp-uniform values (uniform registers); one elected lane issues
+          const uint64_t a_desc = make_desc_k_sw128(smem_u32(smem_a + stage * A_BYTES));
+          const uint64_t b_desc = make_desc_k_sw128(smem_u32(smem_b + stage * B_BYTES));
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               tc_mma_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
