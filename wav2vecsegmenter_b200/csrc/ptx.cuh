@@ -280,22 +280,26 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar, uint16_t cta_mas
 // ------------------------------------------------------------------ math helpers
 // erf-GELU, x * 0.5 (1 + erf(x/sqrt2)), via Abramowitz-Stegun 7.1.28:
 //   erfc(z) ~= (1 + a1 z + ... + a6 z^6)^-16,  z >= 0,  |error| <= 3e-7
-// Six FMAs, four squarings and ONE MUFU (rcp) per element instead of erff()'s ~40 instructions
+// Six FMAs, four squarings, ONE MUFU (rcp) and three more FP ops per element instead of erff()'s
+// ~40 instructions
 // (or 7.1.26's rcp + ex2): the FFN-up epilogue applies this to every accumulator element and has
 // to keep pace with the tensor pipe. Every caller rounds the result to bf16 (rel. 4e-3), against
 // which 3e-7 absolute is invisible.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float p = fmaf(0.0000430638f, z, 0.0002765672f);
-  p = fmaf(p, z, 0.0001520143f);
-  p = fmaf(p, z, 0.0092705272f);
-  p = fmaf(p, z, 0.0422820123f);
-  p = fmaf(p, z, 0.0705230784f);
-  p = fmaf(p, z, 1.0f);
+  // q(|x|) = 2^(1/16) * (1 + a1 z + ... + a6 z^6) with z = |x|/sqrt2 folded into the coefficients,
+  // so q^16 = 2 * (...)^16 and t = 1/q^16 = erfc(z)/2 directly.  gelu = x * Phi(x)
+  //   = 0.5 x + |x| (0.5 - t)          (x >= 0: x (1 - t);  x < 0: x t)
+  const float ax = fabsf(x);
+  float p = fmaf(5.6212996640e-06f, ax, 5.1055209009e-05f);
+  p = fmaf(p, ax, 3.9686137011e-05f);
+  p = fmaf(p, ax, 3.4227392389e-03f);
+  p = fmaf(p, ax, 2.2076998457e-02f);
+  p = fmaf(p, ax, 5.2075163037e-02f);
+  p = fmaf(p, ax, 1.0442737824e+00f);
   p *= p; p *= p; p *= p; p *= p;                  // ^16 (inf for |x| > ~17 -> rcp gives 0)
-  const float half_erfc = 0.5f * __fdividef(1.0f, p);
-  const float cdf = (x >= 0.f) ? (1.0f - half_erfc) : half_erfc;
-  return x * cdf;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(p));
+  return fmaf(ax, 0.5f - t, 0.5f * x);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
