@@ -256,7 +256,7 @@ def run_native(args):
         if tp.exists():
             traffic = json.loads(tp.read_text()).get("kernels", {}).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {
-            "kernel": "gemm_tc_kernel<256,0> FFN-up launches (M=13986 N=4608 K=1024, bias+GELU/ReLU, bf16 out; tcgen05/TMEM/TMA)",
+            "kernel": "gemm_tc2_kernel<bf16-out> FFN-up launches (M=13986 N=4608 K=1024, bias+GELU/ReLU; tcgen05 cta_group::2 / TMEM / TMA)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
             "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
             "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",

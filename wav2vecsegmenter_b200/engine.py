@@ -155,8 +155,10 @@ class SFCEngine:
     @staticmethod
     def _i32(x, device):
         if isinstance(x, torch.Tensor):
+            if x.dtype == torch.int32 and x.is_cuda and x.is_contiguous():
+                return x
             return x.to(device=device, dtype=torch.int32).contiguous()
-        return torch.tensor(list(x), dtype=torch.int32, device=device)
+        return torch.tensor(list(x), dtype=torch.int32).to(device, non_blocking=True)
 
     # ------------------------------------------------------------------ forward
     def encode(self, audio: torch.Tensor, sample_len, norm_len=None, l_max: int | None = None):

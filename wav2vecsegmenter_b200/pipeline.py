@@ -176,20 +176,46 @@ class TalkRunner:
         import torch
 
         eng = self.engine
-        rows = torch.zeros(len(wins), r_max, dtype=torch.float32, device=eng.device)
+        rows = torch.empty(len(wins), r_max, dtype=torch.float32, device=eng.device)
         for b0 in range(0, len(wins), self.device_batch):
             group = wins[b0: b0 + self.device_batch]
             lmax = max(w.n_samples for w in group)
             if lmax < 400:
+                rows[b0: b0 + len(group)].zero_()
                 continue  # shorter than one receptive field: no frames at all
-            stage = torch.zeros(len(group), lmax, dtype=torch.float32, device=eng.device)
-            for k, w in enumerate(group):
-                stage[k, : w.n_samples] = waves_dev[w.talk][w.start: w.end]
-            _, probs = eng.sfc_forward(stage, [w.n_samples for w in group], [w.norm_len for w in group],
-                                       [w.out_len for w in group], lmax)
-            R = probs.shape[1]
-            rows[b0: b0 + len(group), : min(R, r_max)] = probs[:, : min(R, r_max)]
+            first = group[0]
+            step = group[1].start - first.start if len(group) > 1 else lmax
+            regular = (all(w.talk == first.talk for w in group) and step >= lmax
+                       and all(w.start == first.start + k * step for k, w in enumerate(group))
+                       and first.start + (len(group) - 1) * step + lmax <= waves_dev[first.talk].numel())
+            if regular:
+                # consecutive windows of one talk: a strided VIEW of the talk's samples is the batch
+                # (rows may run past a short last window: sample_len masks that)
+                stage = waves_dev[first.talk].as_strided((len(group), lmax), (step, 1), first.start)
+            else:
+                stage = torch.zeros(len(group), lmax, dtype=torch.float32, device=eng.device)
+                for k, w in enumerate(group):
+                    stage[k, : w.n_samples] = waves_dev[w.talk][w.start: w.end]
+            meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
+                                 [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
+            R = eng.frame_stride(lmax)
+            if R == r_max:   # write straight into the row buffer
+                eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax, probs_out=rows[b0: b0 + len(group)],
+                                logits_out=self._logits_scratch(len(group), R))
+            else:
+                _, probs = eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax)
+                rows[b0: b0 + len(group), :R] = probs
+                rows[b0: b0 + len(group), R:].zero_()
         return rows
+
+    def _logits_scratch(self, b: int, r: int):
+        import torch
+
+        buf = getattr(self, "_logits_buf", None)
+        if buf is None or buf.shape[0] < b or buf.shape[1] != r:
+            buf = torch.empty(b, r, dtype=torch.float32, device=self.engine.device)
+            self._logits_buf = buf
+        return buf[:b]
 
     def run(self, waves: list[np.ndarray]) -> list[TalkResult]:
         """waves: one float32 array of raw samples per talk. Returns per-talk probabilities."""
