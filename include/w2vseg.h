@@ -129,11 +129,14 @@ size_t w2vseg_workspace_bytes(const w2vseg_handle* h, int32_t B, int64_t l_max);
  *                lib/datautils.py:88)
  *   l_max        host: max sample_len over the batch (defines R)
  *   hidden_out   device fp32 [B, R, hidden]: encoder output incl. rows >= T(len)
- *   enc_len_out  device int32 [B] or NULL: T(sample_len[b]) */
+ *   enc_len_out  device int32 [B] or NULL: T(sample_len[b])
+ *   included_out device int32 [B] or NULL: CollateFn's `included` (lib/datautils.py:88) decided
+ *                on the device: 0 iff norm_len[b] > 0 and the window's samples sum to zero (such a
+ *                window is not normalised; lib/evaluate.py:109-111 reports its frames as 0) */
 int32_t w2vseg_encode(w2vseg_handle* h, const float* audio, int64_t audio_stride,
                       const int32_t* sample_len, const int32_t* norm_len, int32_t B, int64_t l_max,
-                      float* hidden_out, int32_t* enc_len_out, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      float* hidden_out, int32_t* enc_len_out, int32_t* included_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces model.seg_model(hidden, out_mask) + sigmoid + masking (lib/evaluate.py:72-91).
  *   hidden        device fp32, window b frame t at hidden + b*batch_stride + t*hidden_dim
@@ -152,16 +155,18 @@ int32_t w2vseg_head(w2vseg_handle* h, const float* hidden, int64_t batch_stride,
 int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_stride,
                            const int32_t* sample_len, const int32_t* norm_len,
                            const int32_t* out_len, int32_t B, int64_t l_max, float* logits_out,
-                           float* probs_out, void* workspace, size_t workspace_bytes,
-                           void* stream);
+                           float* probs_out, int32_t* included_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- talk-level reductions (all device pointers) --------------------------------------------- */
 /* talk[0..n_frames) = NaN, then for each window row w: talk[start[w] .. start[w]+count[w]) =
  * (double) rows[w*row_stride .. +count[w]) ; count[w] < 0 writes zeros over -count[w] frames
- * (silent windows). lib/evaluate.py:21-22,100-111. */
+ * (silent windows). If flag_col >= 0, column flag_col of each row holds the window's `included`
+ * flag as a float and a zero there turns the row into a zero-writing one.
+ * lib/evaluate.py:21-22,100-111. */
 int32_t w2vseg_scatter_rows(const float* rows, int64_t row_stride, const int32_t* start,
                             const int32_t* count, int32_t n_rows, double* talk, int64_t n_frames,
-                            void* stream);
+                            int32_t flag_col, void* stream);
 /* in-place sequential fill of the listed NaN frames with the nan-mean of talk[j-2 .. j+2]
  * (lib/evaluate.py:118-125); idx must be sorted ascending. */
 int32_t w2vseg_nanfill(double* talk, int64_t n_frames, const int32_t* idx, int32_t n_idx,

@@ -74,5 +74,4 @@ def test_plan_is_deterministic_and_talk_major():
            [(w.talk, w.tiling, w.start, w.end, w.norm_len, w.out_len) for w in b] and na == nb
     keys = [(w.talk, w.tiling, w.start) for w in a]
     assert keys == sorted(keys)
-    assert all(not w.included and w.norm_len == 0 for w in a if w.talk == 0)   # silent talk
-    assert all(w.included and w.norm_len >= w.n_samples for w in a if w.talk == 1)
+    assert all(w.norm_len >= w.n_samples for w in a)   # silence is detected on the device

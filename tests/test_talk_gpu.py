@@ -148,17 +148,19 @@ def test_talk_reduction_kernels_bit_exact(tiny_engine):
     eng = tiny_engine
     rng = np.random.default_rng(0)
     n = 3351
-    rows = torch.from_numpy(rng.random((5, 1100), dtype=np.float32)).cuda()
-    start = [0, 999, 1998, 2997, 3200]
-    count = [998, 999, -999, 200, 0]          # a gap at 998, a silent window, uncovered tail
-    talk = eng.scatter_rows(rows, start, count, n)
+    rows = torch.from_numpy(rng.random((6, 1100), dtype=np.float32)).cuda()
+    rows[:, -1] = 1.0
+    rows[5, -1] = 0.0                         # device-side `included` flag: row 5 is a silent window
+    start = [0, 999, 1998, 2997, 3200, 3250]
+    count = [998, 999, -999, 200, 0, 50]      # a gap at 998, a silent window, uncovered gaps
+    talk = eng.scatter_rows(rows, start, count, n, flag_col=1099)
     ref = np.full(n, np.nan)
     rc = rows.cpu().numpy()
     for w, (s, c) in enumerate(zip(start, count)):
-        if c > 0:
+        if c > 0 and rc[w, -1] != 0:
             ref[s:s + c] = rc[w, :c]
-        elif c < 0:
-            ref[s:s - c] = 0
+        elif c != 0:
+            ref[s:s + abs(c)] = 0
     got = talk.cpu().numpy()
     assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
     nan_idx = np.flatnonzero(np.isnan(ref))
@@ -269,3 +271,18 @@ def test_long_form_two_hours(tiny_engine, seg):
         if tag != "pthr":
             assert max(r["duration"] for r in recs) <= ALGOS[tag]["max_segment_length"] + 0.2 or tag == "dac"
         yaml.dump(recs, default_flow_style=True)
+
+
+def test_silent_window_reported_as_zero(tiny_engine):
+    """a window of digital silence is `not included` (lib/datautils.py:88): its frames are 0
+    (lib/evaluate.py:109-111) and the neighbouring windows are unaffected"""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    _, wave_f = pcm_wave(3 * 320_000 + 50_000, 21)
+    ref = TalkRunner(tiny_engine, batch_size=14, inference_times=1).run([wave_f])[0].probs
+    silent = wave_f.copy()
+    silent[320_000: 640_000] = 0.0
+    got = TalkRunner(tiny_engine, batch_size=14, inference_times=1).run([silent])[0].probs
+    assert (got[999:1998] == 0).all()
+    assert np.abs(got[:999] - ref[:999]).max() < 1e-6 and np.abs(got[1998:] - ref[1998:]).max() < 1e-6
+    assert (ref[999:1998] > 0).any()

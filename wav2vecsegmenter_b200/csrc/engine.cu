@@ -59,7 +59,7 @@ struct Slot {
 };
 
 struct Workspace {
-  float2* stats; int32_t* enc_len; double2* stat_partial;
+  float2* stats; int32_t* enc_len; int32_t* included; double2* stat_partial;
   bf16* conv[7];
   bf16* feat; float* h; bf16* zpad; bf16* xn; bf16* qkv; bf16* ctx; bf16* mid;
   size_t bytes;
@@ -241,6 +241,7 @@ Workspace carve(const w2vseg_handle* h, uint8_t* base, int B, int R) {
   const int D = h->D, CD = h->cfg.conv_dim;
   w.stats = reinterpret_cast<float2*>(take(sizeof(float2) * B));
   w.enc_len = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * B));
+  w.included = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * B));
   w.stat_partial = reinterpret_cast<double2*>(take(sizeof(double2) * 64 * B));
   for (int l = 0; l < 7; ++l) {
     const size_t rows = M << (6 - l);
@@ -289,7 +290,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
   const int64_t M = (int64_t)B * R;
 
   W2V_TRY(window_stats_launch(audio, audio_stride, sample_len, norm_len, B, w.stat_partial, w.stats,
-                              w.enc_len, st));
+                              w.enc_len, w.included, st));
 
   // conv feature extractor (HF:382-419). Layer l activations: channels-last bf16 [B*R*2^(6-l), 512].
   const int R0 = R << 6;
@@ -544,7 +545,7 @@ static int check_ws(const w2vseg_handle* h, void* workspace, size_t workspace_by
 
 int32_t w2vseg_encode(w2vseg_handle* h, const float* audio, int64_t audio_stride,
                       const int32_t* sample_len, const int32_t* norm_len, int32_t B, int64_t l_max,
-                      float* hidden_out, int32_t* enc_len_out, void* workspace,
+                      float* hidden_out, int32_t* enc_len_out, int32_t* included_out, void* workspace,
                       size_t workspace_bytes, void* stream) {
   W2V_TRY(check_ready(h));
   W2V_REQUIRE(audio && sample_len && norm_len && hidden_out, "encode: null argument");
@@ -559,6 +560,8 @@ int32_t w2vseg_encode(w2vseg_handle* h, const float* audio, int64_t audio_stride
                                  cudaMemcpyDeviceToDevice, st));
   if (enc_len_out != nullptr)
     W2V_CHECK_CUDA(cudaMemcpyAsync(enc_len_out, w.enc_len, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  if (included_out != nullptr)
+    W2V_CHECK_CUDA(cudaMemcpyAsync(included_out, w.included, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -581,8 +584,8 @@ int32_t w2vseg_head(w2vseg_handle* h, const float* hidden, int64_t batch_stride,
 int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_stride,
                            const int32_t* sample_len, const int32_t* norm_len,
                            const int32_t* out_len, int32_t B, int64_t l_max, float* logits_out,
-                           float* probs_out, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           float* probs_out, int32_t* included_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   W2V_TRY(check_ready(h));
   W2V_REQUIRE(audio && sample_len && norm_len && out_len, "sfc_forward: null argument");
   W2V_REQUIRE(B > 0 && l_max >= 400 && audio_stride >= l_max,
@@ -594,16 +597,19 @@ int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_s
   W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
   W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
   W2V_TRY(run_head(h, w, w.h, B, R, out_len, logits_out, probs_out, st));
+  if (included_out != nullptr)
+    W2V_CHECK_CUDA(cudaMemcpyAsync(included_out, w.included, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 // ---- talk-level reductions -------------------------------------------------------------------
 int32_t w2vseg_scatter_rows(const float* rows, int64_t row_stride, const int32_t* start,
                             const int32_t* count, int32_t n_rows, double* talk, int64_t n_frames,
-                            void* stream) {
+                            int32_t flag_col, void* stream) {
   W2V_REQUIRE(talk != nullptr && n_frames >= 0 && n_rows >= 0, "scatter_rows: bad argument");
   W2V_REQUIRE(n_rows == 0 || (rows && start && count), "scatter_rows: null argument");
-  return scatter_rows_launch(rows, row_stride, start, count, n_rows, talk, n_frames, (cudaStream_t)stream);
+  W2V_REQUIRE(flag_col < row_stride, "scatter_rows: flag column outside the row");
+  return scatter_rows_launch(rows, row_stride, start, count, n_rows, talk, n_frames, flag_col, (cudaStream_t)stream);
 }
 int32_t w2vseg_nanfill(double* talk, int64_t n_frames, const int32_t* idx, int32_t n_idx, void* stream) {
   W2V_REQUIRE(talk != nullptr && (n_idx == 0 || idx != nullptr), "nanfill: null argument");

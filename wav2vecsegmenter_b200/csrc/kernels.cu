@@ -67,13 +67,15 @@ window_stats_partial_kernel(const float* __restrict__ audio, long long audio_str
 __global__ void window_stats_final_kernel(const double2* __restrict__ partial,
                                           const int* __restrict__ sample_len,
                                           const int* __restrict__ norm_len, int B,
-                                          float2* __restrict__ stats, int* __restrict__ enc_len) {
+                                          float2* __restrict__ stats, int* __restrict__ enc_len,
+                                          int* __restrict__ included) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (enc_len != nullptr) enc_len[b] = conv_frames(sample_len[b]);
   const int nl = norm_len[b];
   if (nl <= 0) {
     stats[b] = make_float2(0.f, 1.f);
+    included[b] = 1;
     return;
   }
   double s = 0.0, q = 0.0;
@@ -82,6 +84,14 @@ __global__ void window_stats_final_kernel(const double2* __restrict__ partial,
     s += p.x;
     q += p.y;
   }
+  // lib/datautils.py:88: a window whose samples sum to zero is "not included": it is not
+  // normalised and its frames are reported as probability 0 (lib/evaluate.py:109-111)
+  if (s == 0.0) {
+    stats[b] = make_float2(0.f, 1.f);
+    included[b] = 0;
+    return;
+  }
+  included[b] = 1;
   const double mean = s / (double)nl;
   const double var = (q - (double)nl * mean * mean) / (double)(nl - 1);
   stats[b] = make_float2((float)mean, (float)(1.0 / sqrt(var)));
@@ -404,10 +414,12 @@ __global__ void fill_nan_kernel(double* __restrict__ talk, long long n) {
 __global__ void __launch_bounds__(256)
 scatter_rows_kernel(const float* __restrict__ rows, long long row_stride,
                     const int* __restrict__ start, const int* __restrict__ count,
-                    double* __restrict__ talk, long long n_frames) {
+                    double* __restrict__ talk, long long n_frames, int flag_col) {
   const int w = blockIdx.x;
-  const int cnt = count[w];
+  int cnt = count[w];
   const long long s0 = start[w];
+  // optional per-row "included" flag stored as a float in column flag_col of the row
+  if (flag_col >= 0 && cnt > 0 && rows[(long long)w * row_stride + flag_col] == 0.f) cnt = -cnt;
   if (cnt >= 0) {
     const float* r = rows + (long long)w * row_stride;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
@@ -484,14 +496,14 @@ inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 
 // ---------------------------------------------------------------------------------------------
 int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
                         const int32_t* norm_len, int B, double2* partial, float2* stats,
-                        int32_t* enc_len, cudaStream_t s) {
+                        int32_t* enc_len, int32_t* included, cudaStream_t s) {
   if (B <= 0) return 0;
   ProfScope ps(s, "window_stats");
   window_stats_partial_kernel<<<dim3(STAT_CHUNKS, B), 256, 0, s>>>(audio, audio_stride, sample_len,
                                                                   norm_len, partial);
   W2V_CHECK_LAUNCH();
   window_stats_final_kernel<<<(B + 127) / 128, 128, 0, s>>>(partial, sample_len, norm_len, B, stats,
-                                                            enc_len);
+                                                            enc_len, included);
   W2V_CHECK_LAUNCH();
   return 0;
 }
@@ -601,13 +613,13 @@ int weightnorm_scale_launch(const float* v, const float* g, int OI, int J, float
 
 int scatter_rows_launch(const float* rows, int64_t row_stride, const int32_t* start,
                         const int32_t* count, int n_rows, double* talk, int64_t n_frames,
-                        cudaStream_t s) {
+                        int flag_col, cudaStream_t s) {
   if (n_frames > 0) {
     fill_nan_kernel<<<blocks_for(n_frames, 256), 256, 0, s>>>(talk, n_frames);
     W2V_CHECK_LAUNCH();
   }
   if (n_rows > 0) {
-    scatter_rows_kernel<<<n_rows, 256, 0, s>>>(rows, row_stride, start, count, talk, n_frames);
+    scatter_rows_kernel<<<n_rows, 256, 0, s>>>(rows, row_stride, start, count, talk, n_frames, flag_col);
     W2V_CHECK_LAUNCH();
   }
   return 0;

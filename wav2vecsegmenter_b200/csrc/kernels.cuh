@@ -9,7 +9,7 @@ namespace w2v {
 // stats[b] = (mean, 1/std) over the zero-padded row of norm_len[b] samples; (0, 1) if norm_len==0.
 int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
                         const int32_t* norm_len, int B, double2* partial /*[B*64] scratch*/,
-                        float2* stats, int32_t* enc_len, cudaStream_t s);
+                        float2* stats, int32_t* enc_len, int32_t* included, cudaStream_t s);
 
 // conv layer 0 (1->512, k=10, s=5) + LayerNorm(512) + GELU, input normalisation fused (HF:281-299).
 // out bf16 [B*R0, 512], channels-last.
@@ -65,7 +65,7 @@ int weightnorm_scale_launch(const float* v, const float* g, int OI, int J, float
 // ---- talk-level reductions (see w2vseg.h) ---------------------------------------------------
 int scatter_rows_launch(const float* rows, int64_t row_stride, const int32_t* start,
                         const int32_t* count, int n_rows, double* talk, int64_t n_frames,
-                        cudaStream_t s);
+                        int flag_col, cudaStream_t s);
 int nanfill_launch(double* talk, int64_t n_frames, const int32_t* idx, int n_idx, cudaStream_t s);
 int overlap_average_launch(const double* tilings, int n_tilings, int64_t n_frames, double* out,
                            cudaStream_t s);

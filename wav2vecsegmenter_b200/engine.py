@@ -176,7 +176,7 @@ class SFCEngine:
         ws = self._workspace(B, l_max)
         nat.check(
             self.lib.w2vseg_encode(self._h, audio.data_ptr(), audio.stride(0), sl.data_ptr(), nl.data_ptr(),
-                                   B, l_max, hidden.data_ptr(), enc_len.data_ptr(), ws.data_ptr(),
+                                   B, l_max, hidden.data_ptr(), enc_len.data_ptr(), None, ws.data_ptr(),
                                    ws.numel(), self._stream()),
             "w2vseg_encode",
         )
@@ -201,8 +201,10 @@ class SFCEngine:
         return logits, probs
 
     def sfc_forward(self, audio: torch.Tensor, sample_len, norm_len, out_len, l_max: int,
-                    logits_out: torch.Tensor | None = None, probs_out: torch.Tensor | None = None):
-        """fused encode + head. Returns (logits, probs), each fp32 [B, R]."""
+                    logits_out: torch.Tensor | None = None, probs_out: torch.Tensor | None = None,
+                    included_out: torch.Tensor | None = None):
+        """fused encode + head. Returns (logits, probs), each fp32 [B, R]. included_out (optional
+        int32 [B] on the device) receives CollateFn's `included` flag, decided on the device."""
         assert audio.is_cuda and audio.dtype == torch.float32 and audio.dim() == 2 and audio.stride(1) == 1
         B = audio.shape[0]
         sl = self._i32(sample_len, self.device)
@@ -217,22 +219,23 @@ class SFCEngine:
         nat.check(
             self.lib.w2vseg_sfc_forward(self._h, audio.data_ptr(), audio.stride(0), sl.data_ptr(),
                                         nl.data_ptr(), ol.data_ptr(), B, int(l_max),
-                                        logits_out.data_ptr(), probs_out.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), self._stream()),
+                                        logits_out.data_ptr(), probs_out.data_ptr(), nat.ptr(included_out),
+                                        ws.data_ptr(), ws.numel(), self._stream()),
             "w2vseg_sfc_forward",
         )
         return logits_out, probs_out
 
     # ------------------------------------------------------------------ talk-level reductions
-    def scatter_rows(self, rows: torch.Tensor, start, count, n_frames: int) -> torch.Tensor:
-        """rows fp32 [W, stride] -> talk vector fp64 [n_frames] (NaN where no window wrote)"""
+    def scatter_rows(self, rows: torch.Tensor, start, count, n_frames: int, flag_col: int = -1) -> torch.Tensor:
+        """rows fp32 [W, stride] -> talk vector fp64 [n_frames] (NaN where no window wrote);
+        flag_col >= 0: that column of each row holds the window's `included` flag"""
         assert rows.is_cuda and rows.dtype == torch.float32 and rows.stride(-1) == 1
         st = self._i32(start, self.device)
         ct = self._i32(count, self.device)
         talk = torch.empty(n_frames, dtype=torch.float64, device=self.device)
         nat.check(
             self.lib.w2vseg_scatter_rows(rows.data_ptr(), rows.stride(0), st.data_ptr(), ct.data_ptr(),
-                                         st.numel(), talk.data_ptr(), n_frames, self._stream()),
+                                         st.numel(), talk.data_ptr(), n_frames, int(flag_col), self._stream()),
             "w2vseg_scatter_rows",
         )
         return talk

@@ -158,30 +158,31 @@ class TalkRunner:
 
     # -------------------------------------------------------------------------------------
     def plan(self, waves: list[np.ndarray]) -> tuple[list[Window], list[int]]:
-        import torch
-
+        """global window list (talk-major, tiling-major). CollateFn's `included` flag
+        (lib/datautils.py:88, "sample sum != 0") is decided on the device by the forward pass, so
+        the host never has to touch the samples; every window is planned as included."""
         wins, n_frames = [], []
         for t, wave in enumerate(waves):
             dur = len(wave)
             n_frames.append(samples_to_frames(dur))
-            wt = torch.from_numpy(np.ascontiguousarray(wave))
             for i in range(self.inference_times):
-                s, e = tiling_bounds(dur, self.segment_sec, self.inference_times, i)
-                inc = [bool(wt[a:b].sum()) for a, b in zip(s, e)]  # lib/datautils.py:88
-                wins += plan_tiling(dur, self.segment_sec, self.inference_times, i, self.batch_size, t, inc)
+                wins += plan_tiling(dur, self.segment_sec, self.inference_times, i, self.batch_size, t)
         return wins, n_frames
 
     def _forward_rows(self, waves_dev, wins: list[Window], r_max: int):
-        """probability rows fp32 [len(wins), r_max] on the device for the given windows"""
+        """probability rows fp32 [len(wins), r_max + 1] on the device for the given windows; the
+        last column carries the window's `included` flag (1.0 / 0.0)"""
         import torch
 
         eng = self.engine
-        rows = torch.empty(len(wins), r_max, dtype=torch.float32, device=eng.device)
+        rows = torch.empty(len(wins), r_max + 1, dtype=torch.float32, device=eng.device)
+        flags = torch.empty(len(wins), dtype=torch.int32, device=eng.device)
         for b0 in range(0, len(wins), self.device_batch):
             group = wins[b0: b0 + self.device_batch]
             lmax = max(w.n_samples for w in group)
             if lmax < 400:
                 rows[b0: b0 + len(group)].zero_()
+                flags[b0: b0 + len(group)] = 1
                 continue  # shorter than one receptive field: no frames at all
             first = group[0]
             step = group[1].start - first.start if len(group) > 1 else lmax
@@ -199,13 +200,13 @@ class TalkRunner:
             meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
                                  [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
             R = eng.frame_stride(lmax)
-            if R == r_max:   # write straight into the row buffer
-                eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax, probs_out=rows[b0: b0 + len(group)],
-                                logits_out=self._logits_scratch(len(group), R))
-            else:
-                _, probs = eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax)
-                rows[b0: b0 + len(group), :R] = probs
-                rows[b0: b0 + len(group), R:].zero_()
+            _, probs = eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax,
+                                       logits_out=self._logits_scratch(len(group), R),
+                                       included_out=flags[b0: b0 + len(group)])
+            rows[b0: b0 + len(group), :R] = probs
+            if R < r_max:
+                rows[b0: b0 + len(group), R:r_max].zero_()
+        rows[:, r_max] = flags.to(torch.float32)
         return rows
 
     def _logits_scratch(self, b: int, r: int):
@@ -254,7 +255,7 @@ class TalkRunner:
                 sub = [wins[k] for k in idx]
                 st, ct, nan_idx = scatter_plan(sub, n)
                 talk_rows = rows[idx[0]: idx[-1] + 1] if idx else rows[:0]
-                talk = eng.scatter_rows(talk_rows, st, ct, n)
+                talk = eng.scatter_rows(talk_rows, st, ct, n, flag_col=talk_rows.shape[1] - 1)
                 eng.nanfill(talk, nan_idx)
                 tilings[i] = talk
             avg = eng.overlap_average(tilings)
