@@ -127,8 +127,10 @@ def test_layernorm(lib, C, in_f32, act):
     ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
     if act:
         ref = torch.nn.functional.gelu(ref)
-    assert (out.float() - ref).abs().max().item() < 4e-2
-    assert (out.float() - ref).abs().mean().item() < 3e-3
+    # bf16 output: half an ulp is 2^-9 relative; GELU adds <= 5e-4 relative (MUFU.TANH)
+    err = (out.float() - ref).abs()
+    assert (err <= 1e-2 + 6e-3 * ref.abs()).all(), f"max abs err {err.max().item()}"
+    assert err.mean().item() < 3e-3
 
 
 @pytest.mark.parametrize("impl", ["w2vseg_attention", "w2vseg_attention_mma"])

@@ -278,28 +278,22 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar, uint16_t cta_mas
 }
 
 // ------------------------------------------------------------------ math helpers
-// erf-GELU, x * 0.5 (1 + erf(x/sqrt2)), via Abramowitz-Stegun 7.1.28:
-//   erfc(z) ~= (1 + a1 z + ... + a6 z^6)^-16,  z >= 0,  |error| <= 3e-7
-// Six FMAs, four squarings, ONE MUFU (rcp) and three more FP ops per element instead of erff()'s
-// ~40 instructions
-// (or 7.1.26's rcp + ex2): the FFN-up epilogue applies this to every accumulator element and has
-// to keep pace with the tensor pipe. Every caller rounds the result to bf16 (rel. 4e-3), against
-// which 3e-7 absolute is invisible.
+// erf-GELU, x * Phi(x) with Phi(x) = 0.5 (1 + erf(x/sqrt2)), evaluated as
+//     Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4)))
+// with (c0, c1, c2) fitted to the erf form itself (NOT the usual "tanh GELU" constants): max abs
+// error of gelu 3.0e-5 with an exact tanh, ~5e-4 * |gelu| with MUFU.TANH (rel. 2^-11). Every caller
+// rounds the result to bf16 (rel. 2^-9), against which that is a quarter of a rounding step.
+// 6 FP ops + ONE MUFU per element: the FFN-up GEMM applies this to every accumulator element in
+// its epilogue and has to keep pace with the tensor pipe (erff() is ~40 instructions, the
+// Abramowitz-Stegun 7.1.28 form used before 14 + 1 MUFU).
 __device__ __forceinline__ float gelu_erf(float x) {
-  // q(|x|) = 2^(1/16) * (1 + a1 z + ... + a6 z^6) with z = |x|/sqrt2 folded into the coefficients,
-  // so q^16 = 2 * (...)^16 and t = 1/q^16 = erfc(z)/2 directly.  gelu = x * Phi(x)
-  //   = 0.5 x + |x| (0.5 - t)          (x >= 0: x (1 - t);  x < 0: x t)
-  const float ax = fabsf(x);
-  float p = fmaf(5.6212996640e-06f, ax, 5.1055209009e-05f);
-  p = fmaf(p, ax, 3.9686137011e-05f);
-  p = fmaf(p, ax, 3.4227392389e-03f);
-  p = fmaf(p, ax, 2.2076998457e-02f);
-  p = fmaf(p, ax, 5.2075163037e-02f);
-  p = fmaf(p, ax, 1.0442737824e+00f);
-  p *= p; p *= p; p *= p; p *= p;                  // ^16 (inf for |x| > ~17 -> rcp gives 0)
+  const float x2 = x * x;
+  float p = fmaf(-0.00035854941503117723f, x2, 0.03704889695510829f);
+  p = fmaf(p, x2, 0.7974606740658886f);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(p));
-  return fmaf(ax, 0.5f - t, 0.5f * x);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
