@@ -12,6 +12,8 @@ from wav2vecsegmenter_b200 import _native as n  # noqa: E402
 lib = n.load()
 M = 14000
 shapes = [("ffn_up", 4608, 1024, 1, 0), ("ffn_down", 1024, 4608, 0, 1), ("qkv", 3072, 1024, 0, 0)]
+if os.environ.get("MORE"):
+    shapes += [("attn_out", 1024, 1024, 0, 1), ("attn_out_bf16out", 1024, 1024, 0, 0), ("conv_k3_l1", 512, 1536, 0, 0)]
 g = torch.Generator(device="cuda").manual_seed(0)
 BN = int(os.environ.get("BLOCK_N", "256"))
 for name, N, K, act, f32 in shapes:

@@ -6,9 +6,12 @@ entry point fails loudly on a machine without an sm_100 GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libw2vseg.so"
+# W2VSEG_LIB points the loader at another BUILD of the same library (kernel A/B experiments under
+# experiments/); it is never a fallback: the file must exist and export the whole ABI.
+LIB_PATH = Path(os.environ.get("W2VSEG_LIB") or Path(__file__).resolve().parent / "csrc" / "libw2vseg.so")
 
 _lib = None
 

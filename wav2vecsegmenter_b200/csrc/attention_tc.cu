@@ -16,6 +16,8 @@
 //               tile and PV of the current one overlap the exponentials (the MUFU-bound part).
 // Rescaling is lazy (as in FlashAttention-4): the running max used in the exponent is only
 // advanced when the tile max exceeds it by more than 2^8, so O is rarely touched after tile 0.
+#include <cstdlib>
+#include <cstring>
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -375,6 +377,13 @@ int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int h
   if (B <= 0 || R <= 0) return 0;
   W2V_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim %d unsupported (64 / 128)",
               head_dim);
+  if (head_dim == 64) {
+    static const bool use_v15 = [] {
+      const char* e = getenv("W2VSEG_ATT64");
+      return e != nullptr && strcmp(e, "v15") == 0;
+    }();
+    if (!use_v15) return attention_tc64_launch(qkv, B, R, heads, kv_len, scale, ctx, s);
+  }
   const int D = heads * head_dim;
   CUtensorMap tm;
   W2V_TRY(make_tmap_2d_bf16(&tm, qkv, (uint64_t)3 * D, (uint64_t)B * R, (uint64_t)3 * D, 64, AT_BN));

@@ -45,6 +45,10 @@ int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head
 // same contract, tcgen05 / TMEM / TMA implementation (attention_tc.cu) — the product path
 int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
                         const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s);
+// head_dim 64 specialisation with 8 column-split softmax warps (attention_tc64.cu); reached through
+// attention_tc_launch unless W2VSEG_ATT64=v15 selects the 4-warp kernel for A/B measurements
+int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, const int32_t* kv_len,
+                          float scale, __nv_bfloat16* ctx, cudaStream_t s);
 
 // ---- weight packing -----------------------------------------------------------------------
 // dst_bf16[r*ld_dst + c] = src[r*cols + c] * scale
