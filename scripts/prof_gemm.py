@@ -13,7 +13,8 @@ lib = n.load()
 M = 14000
 shapes = [("ffn_up", 4608, 1024, 1, 0), ("ffn_down", 1024, 4608, 0, 1), ("qkv", 3072, 1024, 0, 0)]
 if os.environ.get("MORE"):
-    shapes += [("attn_out", 1024, 1024, 0, 1), ("attn_out_bf16out", 1024, 1024, 0, 0), ("conv_k3_l1", 512, 1536, 0, 0)]
+    shapes += [("attn_out", 1024, 1024, 0, 1), ("attn_out_inplace", 1024, 1024, 0, 2), ("ffn_down_inplace", 1024, 4608, 0, 2),
+               ("attn_out_bf16out", 1024, 1024, 0, 0), ("conv_k3_l1", 512, 1536, 0, 0)]
 g = torch.Generator(device="cuda").manual_seed(0)
 BN = int(os.environ.get("BLOCK_N", "256"))
 for name, N, K, act, f32 in shapes:
@@ -22,6 +23,8 @@ for name, N, K, act, f32 in shapes:
     bias = torch.randn(N, device="cuda", generator=g)
     resid = torch.randn(M, N, device="cuda", generator=g) if f32 else None
     out = torch.empty(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    if f32 == 2:  # the engine's form: h += A W^T + b (out aliases resid)
+        out, f32 = resid, 1
     NW, NT = (1, 1) if os.environ.get('NCU') else (3, 10)
     for _ in range(NW):
         n.check(lib.w2vseg_gemm(n.ptr(A), n.ptr(W), M, N, K, n.ptr(bias), act, n.ptr(resid), n.ptr(out),

@@ -74,6 +74,20 @@ def test_gemm(lib, M, N, K, act, out_f32, use_resid, block_n):
     assert err < tol, f"max abs err {err}"
 
 
+def test_gemm_gelu_large_arguments(lib):
+    """GELU in the GEMM epilogue over the whole fp32-relevant range: |x| up to ~60 (outlier FFN
+    units of trained checkpoints); gelu(x) -> x for large x, -> 0 for large negative x."""
+    M, N, K = 256, 256, 64
+    A = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    A[:, 0] = 1.0
+    W = torch.zeros(N, K, device="cuda", dtype=torch.bfloat16)
+    bias = torch.linspace(-60.0, 60.0, N, device="cuda")     # pre-activation == bias
+    out = _gemm(lib, A, W, bias, 1, None, 1, 256)
+    ref = torch.nn.functional.gelu(bias)[None].expand(M, N)
+    err = (out - ref).abs()
+    assert (err <= 3e-5 + 6e-4 * ref.abs()).all(), f"max abs err {err.max().item()}"
+
+
 def test_gemm_inplace_residual(lib):
     from wav2vecsegmenter_b200 import _native as n
 

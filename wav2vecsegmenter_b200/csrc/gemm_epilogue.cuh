@@ -40,7 +40,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
     const long long w = orow / p.mask_period;
     zero_row = (int)(orow - w * p.mask_period) >= __ldg(p.mask_len + w);
   }
-  const bool use_resid = OUT_F32 && p.resid != nullptr;
+  // in-place residual (out == resid, every residual GEMM of the engine): h += acc + bias as a
+  // fire-and-forget vector reduction at L2 — the epilogue never waits for a residual load
+  const bool use_red = OUT_F32 && p.resid != nullptr && p.resid == p.out && p.ld_resid == p.ld_out;
+  const bool use_resid = OUT_F32 && p.resid != nullptr && !use_red;
 
   float4 res[2][8];
   if constexpr (OUT_F32) {
@@ -140,8 +143,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
             const float4 rv = res[u & 1][k];
             f.x += rv.x; f.y += rv.y; f.z += rv.z; f.w += rv.w;
           }
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ld_out + col0 +
-                                     c_chk * 4) = f;
+          float* dst = reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ld_out + col0 + c_chk * 4;
+          if (use_red)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y),
+                         "f"(f.z), "f"(f.w)
+                         : "memory");
+          else
+            *reinterpret_cast<float4*>(dst) = f;
         } else {
           *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ld_out +
                                     col0 + c_chk * 8) = x;

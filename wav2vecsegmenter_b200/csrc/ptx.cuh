@@ -283,11 +283,14 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar, uint16_t cta_mas
 // with (c0, c1, c2) fitted to the erf form itself (NOT the usual "tanh GELU" constants): max abs
 // error of gelu 3.0e-5 with an exact tanh, ~5e-4 * |gelu| with MUFU.TANH (rel. 2^-11). Every caller
 // rounds the result to bf16 (rel. 2^-9), against which that is a quarter of a rounding step.
-// 6 FP ops + ONE MUFU per element: the FFN-up GEMM applies this to every accumulator element in
+// x^2 is clamped to 36: the fitted polynomial is only monotone up to x^2 ~ 51 (its x^4 coefficient
+// is negative, so unclamped it changes sign at |x| ~ 11 and the function would return 0 for large
+// positive x); at |x| = 6 the tanh argument is already 10, i.e. tanh = +-1 to fp32 precision.
+// 7 FP ops + ONE MUFU per element: the FFN-up GEMM applies this to every accumulator element in
 // its epilogue and has to keep pace with the tensor pipe (erff() is ~40 instructions, the
 // Abramowitz-Stegun 7.1.28 form used before 14 + 1 MUFU).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, 36.f);
   float p = fmaf(-0.00035854941503117723f, x2, 0.03704889695510829f);
   p = fmaf(p, x2, 0.7974606740658886f);
   float t;
