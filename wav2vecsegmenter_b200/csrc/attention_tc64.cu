@@ -11,13 +11,15 @@
 // warp w+4 columns 64..127 of the SAME 32 query rows. That halves every per-warp latency chain,
 // doubles the warps per scheduler (2 CTAs per SM -> 16 softmax warps) and lets the 64 scores stay
 // in registers between the max and the exponentials. The two warps agree on the row max through a
-// 512-byte bf16 exchange in shared memory and one 64-thread named barrier per tile (any common
-// shift is a valid softmax stabiliser, so the bf16 rounding of the shift is harmless); row sums
-// stay per-warp until the end.
+// small fp32 exchange in shared memory and one
+// 64-thread named barrier per tile; row sums stay per-warp until the end. P goes to TMEM as packed
+// bf16x2 (64 columns) and is the A operand of a TS-form MMA: shared memory only carries Q, K and V
+// (with P in shared memory the tile needs ~1150 cycles of shared-memory bandwidth per SM, more
+// than the 1024 cycles of MUFU work: measured 121 -> 113 us).
 //
-//   warps 0..7  softmax (thread = one query row x 64 keys), P -> K-major SW128 shared memory
+//   warps 0..7  softmax (thread = one query row x 64 keys), P -> TMEM (tcgen05.st 32x32b)
 //   warp 8      TMA producer (Q once, K/V double-buffered) + MMA issuer (warp-uniform, elect_one)
-//   TMEM        S 128 columns fp32 | O 64 columns fp32   (256 allocated, two CTAs per SM)
+//   TMEM        S 128 columns fp32 | O 64 columns fp32 | P 64 columns bf16x2   (two CTAs per SM)
 // Rescaling is lazy (FlashAttention-4): the exponent's running max only advances when a tile max
 // exceeds it by more than 2^8. Replaces Wav2Vec2Attention's softmax(QK^T*scale + key mask) V
 // (HF:500-549).
@@ -34,18 +36,17 @@ constexpr int A6_DH = 64;
 constexpr int A6_THREADS = 288;   // 8 softmax warps + 1 TMA/MMA warp
 constexpr int A6_CTRL_WARP = 8;
 constexpr int A6_TILE_BYTES = A6_BN * A6_DH * 2;       // 16 KB: one Q / K / V tile
-constexpr int A6_P_BYTES = A6_BM * A6_BN * 2;          // 32 KB
 constexpr int A6_OFF_Q = 0;
 constexpr int A6_OFF_K = A6_OFF_Q + A6_TILE_BYTES;     // 2 buffers
 constexpr int A6_OFF_V = A6_OFF_K + 2 * A6_TILE_BYTES; // 2 buffers
-constexpr int A6_OFF_P = A6_OFF_V + 2 * A6_TILE_BYTES;
-constexpr int A6_OFF_BAR = A6_OFF_P + A6_P_BYTES;      // 9 mbarriers + TMEM slot (80 B)
-constexpr int A6_OFF_X = A6_OFF_BAR + 128;             // bf16 [2][128] row-max exchange
-// no alignment slack: 2 x (112 KB + 640 B + 1 KB reserved) fit one SM's 228 KB; the kernel traps
-// if the dynamic smem base is not 1024-byte aligned.
-constexpr int A6_SMEM_BYTES = A6_OFF_X + 512;
+constexpr int A6_OFF_BAR = A6_OFF_V + 2 * A6_TILE_BYTES;   // 9 mbarriers + TMEM slot (80 B)
+constexpr int A6_OFF_X = A6_OFF_BAR + 128;             // fp32 [2 tile parities][2 halves][128] row max
+constexpr int A6_OFF_L = A6_OFF_X + 2048;              // fp32 [2 halves][128] row sums (epilogue)
+// the kernel traps if the dynamic smem base is not 1024-byte aligned (no alignment slack)
+constexpr int A6_SMEM_BYTES = A6_OFF_L + 1024;
 constexpr int A6_TMEM_COLS = 256;
 constexpr int A6_O_COL = 128;
+constexpr int A6_P_COL = 192;     // P as packed bf16x2: 64 columns = 128 keys (A operand of P V)
 constexpr float A6_RESCALE_THRESHOLD = 8.0f;           // log2 units
 
 __device__ __forceinline__ float ex2a(float x) {
@@ -90,6 +91,19 @@ __device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, float (&r)[64]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 // 8-column TMEM load / store: the (rare) rescale of O runs in small chunks so that it does not
 // push the 64 live scores out of the register file
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -129,7 +143,6 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
   uint8_t* sQ = smem + A6_OFF_Q;
   uint8_t* sK = smem + A6_OFF_K;
   uint8_t* sV = smem + A6_OFF_V;
-  uint8_t* sP = smem + A6_OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;   // [2]
@@ -139,7 +152,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
   uint64_t* p_full = bars + 7;
   uint64_t* pv_done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem + A6_OFF_X);   // [2][128]
+  float* xch = reinterpret_cast<float*>(smem + A6_OFF_X);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * A6_BM;
@@ -201,7 +214,6 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
       constexpr uint32_t idesc_o = make_idesc_bf16(A6_BM, A6_DH) | (1u << 16);  // B (=V) MN-major
       const uint64_t q_desc = make_desc_k_sw128(smem_u32(sQ));
       const uint64_t k_desc0 = make_desc_k_sw128(smem_u32(sK));
-      const uint64_t p_desc = make_desc_k_sw128(smem_u32(sP));
       const uint64_t v_desc0 = desc_mn_sw128(smem_u32(sV), A6_BN * 128);
 
       auto issue_s = [&](int j) {
@@ -229,6 +241,12 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
           tc_fence_after();
           issue_s(j + 1);
           A6_T(0, 2);   // S(j+1) issued
+#ifdef A6_TRACE
+          if (traced) {                                // MMA round trip: issue -> completion visible
+            mbar_wait(s_full, (uint32_t)((j + 1) & 1));
+            A6_T(0, 5);
+          }
+#endif
           // S(j) has retired (the softmax threads read it), so K buffer j&1 can be refilled
           if (j + 2 < n_tiles)
             load_tile(sK + (j & 1) * A6_TILE_BYTES, &k_full[j & 1], kcol, row_base + (j + 2) * A6_BN);
@@ -241,9 +259,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
           const uint64_t vd = v_desc0 + (uint64_t)(((j & 1) * A6_TILE_BYTES) >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < A6_BN / 16; ++kk)
-              tc_mma_ss(tO, p_desc + (uint64_t)(((kk >> 2) * (A6_BM * 128) + (kk & 3) * 32) >> 4),
-                        vd + (uint64_t)((kk * 16 * 128) >> 4), idesc_o, (uint32_t)((j | kk) != 0));
+            for (int kk = 0; kk < A6_BN / 16; ++kk) {
+              tc_mma_ts(tO, tmem_base + A6_P_COL + (uint32_t)(kk * 8), vd + (uint64_t)((kk * 16 * 128) >> 4),
+                        idesc_o, (uint32_t)((j | kk) != 0));
+            }
             tc_commit(pv_done);
             A6_T(0, 4);   // PV issued
           }
@@ -263,9 +282,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS_mine = tS + lane_off + (uint32_t)(hf * 64);
     const uint32_t tO_mine = tO + lane_off + (uint32_t)(hf * 32);
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(hf * (A6_BM * 128) + r * 128);
-    __nv_bfloat16* x_own = xch + hf * 128 + r;
-    const __nv_bfloat16* x_peer = xch + (hf ^ 1) * 128 + r;
+    const uint32_t tP_mine = tmem_base + A6_P_COL + lane_off + (uint32_t)(hf * 32);
+    float* x_own = xch + hf * 128 + r;               // + 256 * (tile parity)
+    const float* x_peer = xch + (hf ^ 1) * 128 + r;
     float m_used = 0.f;                              // running max (log2 units) used in exponents
     float l_sum = 0.f;                               // this warp's half of the row sum
 
@@ -276,6 +295,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
       float s[64];
       tmem_ld_x64(tS_mine, s);
       tc_wait_ld();
+      tc_fence_before();                               // S(j) is in registers: release the S columns
+      __syncwarp();                                    // for QK^T of tile j+1 right away
+      if (lane == 0) mbar_arrive(s_free);
       A6_T(1, 2);   // S in registers
       const int n_valid = klen - j * A6_BN - hf * 64;    // valid keys among this warp's 64 columns
       if (n_valid < 64) {                                // only the last tile has masked keys
@@ -293,16 +315,13 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], s[60 + k]);
-      const __nv_bfloat16 mx_own = __float2bfloat16_rn(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2);
-      *x_own = mx_own;
+      const float mx_own = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+      // the exchange slots alternate with the tile parity: a warp can only reach its write for tile
+      // j+2 after the pair barrier of tile j+1, which its peer enters after reading the slot of tile j
+      x_own[(j & 1) * 256] = mx_own;
       pair_barrier(1 + quarter);
       A6_T(1, 3);   // max + exchange barrier passed
-      const float mx = fmaxf(__bfloat162float(mx_own), __bfloat162float(*x_peer));
-      // S(j) is in registers and the exchange slot has been read: release S for QK^T of tile j+1.
-      // (The next write of the exchange slot happens after s_full(j+1), i.e. after all 8 arrivals.)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
+      const float mx = fmaxf(mx_own, x_peer[(j & 1) * 256]);
 
       float factor = 1.f;
       bool need = false;
@@ -336,24 +355,20 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
       // into the K-major SW128 layout (this warp's 64 keys = one 128-byte row of P half `hf`).
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_used;
-      A6_T(1, 4);   // pv_done(j-1) seen, rescale done
+      {
+        uint32_t pk[32];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = ex2a(fmaf(s[g * 8 + i], scale_log2, neg_m));
-          sum4[i & 3] += p[i];
+        for (int i = 0; i < 32; ++i) {
+          const float e0 = ex2a(fmaf(s[2 * i], scale_log2, neg_m));
+          const float e1 = ex2a(fmaf(s[2 * i + 1], scale_log2, neg_m));
+          sum4[i & 3] += e0 + e1;
+          pk[i] = pack_bf16x2(e0, e1);
         }
-        const uint32_t u0 = pack_bf16x2(p[0], p[1]), u1 = pack_bf16x2(p[2], p[3]);
-        const uint32_t u2 = pack_bf16x2(p[4], p[5]), u3 = pack_bf16x2(p[6], p[7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (uint32_t)((g ^ (r & 7)) << 4)),
-                     "r"(u0), "r"(u1), "r"(u2), "r"(u3)
-                     : "memory");
+        tmem_st_x32(tP_mine, pk);
       }
       l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      fence_proxy_async_smem();                      // generic-proxy stores -> visible to the MMA
-      tc_fence_before();
+      tc_wait_st();
+      tc_fence_before();                             // P (and a rescaled O) ordered before the MMA
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       A6_T(1, 5);   // P stored, arrived
@@ -365,7 +380,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
     if (n_tiles > 0) {
       mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
       tc_fence_after();
-      float* lx = reinterpret_cast<float*>(sP);      // P is dead: fp32 [2][128] row-sum exchange
+      float* lx = reinterpret_cast<float*>(smem + A6_OFF_L);   // fp32 [2][128] row-sum exchange
       lx[hf * 128 + r] = l_sum;
       pair_barrier(1 + quarter);
       const float inv = 1.f / (l_sum + lx[(hf ^ 1) * 128 + r]);
@@ -399,8 +414,8 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
   if (blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7 && threadIdx.x == 0) {
     printf("end %lld\n", clock64() - t_start);
     for (int j = 0; j < 8; ++j)
-      printf("tile %d ctrl: s_free %lld S_issued %lld p_full %lld PV_issued %lld | smax: s_full %lld loaded %lld xchg %lld pvdone %lld arrived %lld\n",
-             j, g_trace[0][j][1], g_trace[0][j][2], g_trace[0][j][3], g_trace[0][j][4], g_trace[1][j][1],
+      printf("tile %d ctrl: s_free %lld S_issued %lld S_done %lld p_full %lld PV_issued %lld | smax: s_full %lld loaded %lld xchg %lld pvdone %lld arrived %lld\n",
+             j, g_trace[0][j][1], g_trace[0][j][2], g_trace[0][j][5], g_trace[0][j][3], g_trace[0][j][4], g_trace[1][j][1],
              g_trace[1][j][2], g_trace[1][j][3], g_trace[1][j][4], g_trace[1][j][5]);
   }
 #endif
