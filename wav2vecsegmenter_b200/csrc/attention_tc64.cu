@@ -36,14 +36,16 @@ constexpr int A6_DH = 64;
 constexpr int A6_THREADS = 288;   // 8 softmax warps + 1 TMA/MMA warp
 constexpr int A6_CTRL_WARP = 8;
 constexpr int A6_TILE_BYTES = A6_BN * A6_DH * 2;       // 16 KB: one Q / K / V tile
-constexpr int A6_OFF_Q = 0;
-constexpr int A6_OFF_K = A6_OFF_Q + A6_TILE_BYTES;     // 2 buffers
+constexpr int A6_OFF_Q = 0;                            // 2 buffers (item parity)
+constexpr int A6_OFF_K = A6_OFF_Q + 2 * A6_TILE_BYTES; // 2 buffers (tile parity)
 constexpr int A6_OFF_V = A6_OFF_K + 2 * A6_TILE_BYTES; // 2 buffers
-constexpr int A6_OFF_BAR = A6_OFF_V + 2 * A6_TILE_BYTES;   // 9 mbarriers + TMEM slot (80 B)
+constexpr int A6_OFF_BAR = A6_OFF_V + 2 * A6_TILE_BYTES;   // 12 mbarriers + TMEM slot
 constexpr int A6_OFF_X = A6_OFF_BAR + 128;             // fp32 [2 tile parities][2 halves][128] row max
-constexpr int A6_OFF_L = A6_OFF_X + 2048;              // fp32 [2 halves][128] row sums (epilogue)
+constexpr int A6_OFF_L = A6_OFF_X + 2048;              // fp32 [2 item parities][2 halves][128] row sums
 // the kernel traps if the dynamic smem base is not 1024-byte aligned (no alignment slack)
-constexpr int A6_SMEM_BYTES = A6_OFF_L + 1024;
+constexpr int A6_OFF_KLEN = A6_OFF_L + 2048;           // int32 [A6_MAX_B] clamped key lengths
+constexpr int A6_MAX_B = 1024;
+constexpr int A6_SMEM_BYTES = A6_OFF_KLEN + A6_MAX_B * 4;
 constexpr int A6_TMEM_COLS = 256;
 constexpr int A6_O_COL = 128;
 constexpr int A6_P_COL = 192;     // P as packed bf16x2: 64 columns = 128 keys (A operand of P V)
@@ -119,21 +121,69 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
                : "memory");
 }
 
-// -DA6_TRACE: clock64 timeline of one CTA (softmax warp 0 and the control warp), printed at exit
+
+// -DA6_TRACE: clock64 timeline of softmax warp 0 of CTA 5 for stream tiles 16..23, printed at exit
 #ifdef A6_TRACE
-__device__ long long g_trace[2][8][8];   // [role][tile][event]
-#define A6_T(role, ev)                                                                     \
-  do {                                                                                     \
-    if (traced && lane == 0 && j < 8) g_trace[role][j][ev] = clock64() - t_start;          \
+__device__ long long g_trace[8][8];
+__device__ long long g_tile_t[4][64];
+__device__ long long g_ep[8];
+#define A6_E(ev) do { if (blockIdx.x == 5 && threadIdx.x == 0 && seq == 2) g_ep[ev] = clock64() - t_cta0; } while (0)
+   // per-tile s_full-seen stamps of 4 sample CTAs
+#define A6_T(ev)                                                                                   \
+  do {                                                                                             \
+    if (blockIdx.x == 5 && threadIdx.x == 0 && g >= 20 && g < 28) g_trace[g - 20][ev] = clock64(); \
   } while (0)
 #else
-#define A6_T(role, ev) do {} while (0)
+#define A6_T(ev) do {} while (0)
+#define A6_E(ev) do {} while (0)
 #endif
 
+// One work item = (window b, head, 128-row query tile). A CTA walks items blockIdx.x, +gridDim.x, ...
+struct Item {
+  int q0, head, b, klen, n_tiles, row_base;
+};
+// kv_len points at the CTA's shared-memory copy of the (clamped) key lengths: a global load here
+// sits on the critical path of every item change (~2000 cycles under the TMA traffic, measured)
+__device__ __forceinline__ Item make_item(int idx, int n_qt, int heads, int R, const int* kv_len) {
+  Item it;
+  const int qt = idx % n_qt;
+  const int bh = idx / n_qt;
+  it.head = bh % heads;
+  it.b = bh / heads;
+  it.q0 = qt * A6_BM;
+  it.klen = kv_len[it.b];
+  it.n_tiles = (it.klen + A6_BN - 1) / A6_BN;
+  it.row_base = it.b * R;
+  return it;
+}
+// Position in this CTA's stream of key tiles (items with no valid key contribute no tile).
+struct Cursor {
+  int idx;      // item index (>= n_items: end of stream)
+  int seq;      // number of non-empty items before this one (Q / row-sum buffer parity)
+  int j;        // key tile within the item
+  Item it;
+};
+__device__ __forceinline__ void cursor_skip_empty(Cursor& c, int n_items, int stride, int n_qt, int heads,
+                                                  int R, const int* kv_len) {
+  while (c.idx < n_items) {
+    c.it = make_item(c.idx, n_qt, heads, R, kv_len);
+    if (c.it.n_tiles > 0) return;
+    c.idx += stride;
+  }
+}
+__device__ __forceinline__ void cursor_next(Cursor& c, int n_items, int stride, int n_qt, int heads, int R,
+                                            const int* kv_len) {
+  if (++c.j < c.it.n_tiles) return;
+  c.j = 0;
+  c.seq += 1;
+  c.idx += stride;
+  cursor_skip_empty(c, n_items, stride, n_qt, heads, R, kv_len);
+}
+
 __global__ void __launch_bounds__(A6_THREADS, 2)
-attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int heads,
-                      const int* __restrict__ kv_len, float scale_log2,
-                      __nv_bfloat16* __restrict__ ctx) {
+attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
+                      int R, int heads, int n_qt, int n_items, int B, const int* __restrict__ kv_len_g,
+                      float scale_log2, __nv_bfloat16* __restrict__ ctx) {
   extern __shared__ uint8_t att_raw[];
   uint8_t* smem = att_raw;
   if ((smem_u32(att_raw) & 1023u) != 0) {
@@ -144,39 +194,39 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
   uint8_t* sK = smem + A6_OFF_K;
   uint8_t* sV = smem + A6_OFF_V;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* q_full = bars + 0;   // [2]
+  uint64_t* k_full = bars + 2;   // [2]
+  uint64_t* v_full = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* s_free = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* pv_done = bars + 9;
+  uint64_t* o_free = bars + 10;
+  uint64_t* stage_free = bars + 11;   // completion k: the output store of item k has read its staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* xch = reinterpret_cast<float*>(smem + A6_OFF_X);   // [2][2][128]
+  float* lxb = reinterpret_cast<float*>(smem + A6_OFF_L);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * A6_BM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
   const int D = heads * A6_DH;
-  const int klen = min(__ldg(kv_len + b), R);
-  const int n_tiles = (klen + A6_BN - 1) / A6_BN;
-  const int row_base = b * R;   // first row of this window in the flat [B*R] row space
+  const int stride = gridDim.x;
+  int* kv_len = reinterpret_cast<int*>(smem + A6_OFF_KLEN);
+  for (int i = threadIdx.x; i < B; i += A6_THREADS) kv_len[i] = min(__ldg(kv_len_g + i), R);
 #ifdef A6_TRACE
-  const bool traced = blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7 && (warp == 0 || warp == A6_CTRL_WARP);
-  const long long t_start = clock64();
+  const long long t_cta0 = clock64();
 #endif
 
   if (warp == A6_CTRL_WARP) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_qkv);
-      mbar_init(q_full, 1);
-      mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
-      mbar_init(&v_full[0], 1); mbar_init(&v_full[1], 1);
+      tma_prefetch_desc(&tmap_out);
+      for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);   // q_full, k_full, v_full
       mbar_init(s_full, 1);
       mbar_init(s_free, 8);      // one elected arrive per softmax warp
       mbar_init(p_full, 8);
       mbar_init(pv_done, 1);
+      mbar_init(o_free, 8);
+      mbar_init(stage_free, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -192,85 +242,98 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
 
   if (warp == A6_CTRL_WARP) {
     // ------------------------------------------------------------ TMA producer + MMA issuer
-    // every lane runs the warp-uniform control flow (descriptors in uniform registers); one elected
-    // lane issues the TMA / MMA / commit instructions.
-    if (n_tiles > 0) {
-      const int qcol = head * A6_DH, kcol = D + head * A6_DH, vcol = 2 * D + head * A6_DH;
-      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col0, int row) {
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bar, A6_TILE_BYTES);
-          tma_load_2d(dst, &tmap_qkv, bar, col0, row);
-        }
-        __syncwarp();
-      };
-      load_tile(sQ, q_full, qcol, row_base + q0);
-      load_tile(sK, &k_full[0], kcol, row_base);
-      load_tile(sV, &v_full[0], vcol, row_base);
-      if (n_tiles > 1) {
-        load_tile(sK + A6_TILE_BYTES, &k_full[1], kcol, row_base + A6_BN);
-        load_tile(sV + A6_TILE_BYTES, &v_full[1], vcol, row_base + A6_BN);
+    // Every lane runs the warp-uniform control flow (descriptors in uniform registers); one elected
+    // lane issues the TMA / MMA / commit instructions. The key tiles of all items of this CTA form
+    // ONE stream g = 0, 1, ...: K/V buffers, S, P and their barriers are indexed by g, so the loads
+    // and the first QK^T of the next item overlap the last tiles and the epilogue of the current one.
+    auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col0, int row) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar, A6_TILE_BYTES);
+        tma_load_2d(dst, &tmap_qkv, bar, col0, row);
       }
-      constexpr uint32_t idesc_s = make_idesc_bf16(A6_BM, A6_BN);
-      constexpr uint32_t idesc_o = make_idesc_bf16(A6_BM, A6_DH) | (1u << 16);  // B (=V) MN-major
-      const uint64_t q_desc = make_desc_k_sw128(smem_u32(sQ));
-      const uint64_t k_desc0 = make_desc_k_sw128(smem_u32(sK));
-      const uint64_t v_desc0 = desc_mn_sw128(smem_u32(sV), A6_BN * 128);
-
-      auto issue_s = [&](int j) {
-        const uint64_t kd = k_desc0 + (uint64_t)(((j & 1) * A6_TILE_BYTES) >> 4);
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < A6_DH / 16; ++kk)
-            tc_mma_ss(tS, q_desc + (uint64_t)((kk * 32) >> 4), kd + (uint64_t)((kk * 32) >> 4), idesc_s,
-                      (uint32_t)(kk != 0));
-          tc_commit(s_full);
-        }
-        __syncwarp();
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      __syncwarp();
+    };
+    Cursor Lc;   // next tile to LOAD (runs two tiles ahead of the PV cursor)
+    Lc.idx = blockIdx.x; Lc.seq = 0; Lc.j = 0;
+    cursor_skip_empty(Lc, n_items, stride, n_qt, heads, R, kv_len);
+    Cursor Sc = Lc;   // next tile whose QK^T is to be issued
+    Cursor Pc = Lc;   // next tile whose PV is to be issued
+    // K(g) [+ Q of its item when g is the item's first tile]; V(g) is loaded separately
+    auto load_k = [&](const Cursor& c, int g) {
+      // the Q buffer doubles as the output staging tile of the item that used it two items ago
+      if (c.j == 0 && c.seq >= 2) mbar_wait(stage_free, (uint32_t)((c.seq - 2) & 1));
+      if (c.j == 0) load_tile(sQ + (c.seq & 1) * A6_TILE_BYTES, &q_full[c.seq & 1], c.it.head * A6_DH, c.it.row_base + c.it.q0);
+      load_tile(sK + (g & 1) * A6_TILE_BYTES, &k_full[g & 1], D + c.it.head * A6_DH, c.it.row_base + c.j * A6_BN);
+    };
+    auto load_v = [&](const Cursor& c, int g) {
+      load_tile(sV + (g & 1) * A6_TILE_BYTES, &v_full[g & 1], 2 * D + c.it.head * A6_DH, c.it.row_base + c.j * A6_BN);
+    };
+    constexpr uint32_t idesc_s = make_idesc_bf16(A6_BM, A6_BN);
+    constexpr uint32_t idesc_o = make_idesc_bf16(A6_BM, A6_DH) | (1u << 16);  // B (=V) MN-major
+    const uint64_t q_desc0 = make_desc_k_sw128(smem_u32(sQ));
+    const uint64_t k_desc0 = make_desc_k_sw128(smem_u32(sK));
+    const uint64_t v_desc0 = desc_mn_sw128(smem_u32(sV), A6_BN * 128);
+    auto issue_s = [&](const Cursor& c, int g) {     // S(g) = Q K^T
+      mbar_wait(&k_full[g & 1], (uint32_t)((g >> 1) & 1));
+      if (c.j == 0) mbar_wait(&q_full[c.seq & 1], (uint32_t)((c.seq >> 1) & 1));
+      if (g > 0) mbar_wait(s_free, (uint32_t)((g - 1) & 1));   // S(g-1) is in the softmax registers
       tc_fence_after();
-      issue_s(0);
+      const uint64_t qd = q_desc0 + (uint64_t)(((c.seq & 1) * A6_TILE_BYTES) >> 4);
+      const uint64_t kd = k_desc0 + (uint64_t)(((g & 1) * A6_TILE_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < A6_DH / 16; ++kk)
+          tc_mma_ss(tS, qd + (uint64_t)((kk * 32) >> 4), kd + (uint64_t)((kk * 32) >> 4), idesc_s,
+                    (uint32_t)(kk != 0));
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
 
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          mbar_wait(&k_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-          mbar_wait(s_free, (uint32_t)(j & 1));      // every softmax warp holds S(j) in registers
-          A6_T(0, 1);   // s_free seen
-          tc_fence_after();
-          issue_s(j + 1);
-          A6_T(0, 2);   // S(j+1) issued
-#ifdef A6_TRACE
-          if (traced) {                                // MMA round trip: issue -> completion visible
-            mbar_wait(s_full, (uint32_t)((j + 1) & 1));
-            A6_T(0, 5);
-          }
-#endif
-          // S(j) has retired (the softmax threads read it), so K buffer j&1 can be refilled
-          if (j + 2 < n_tiles)
-            load_tile(sK + (j & 1) * A6_TILE_BYTES, &k_full[j & 1], kcol, row_base + (j + 2) * A6_BN);
+    if (Lc.idx < n_items) {
+      // prologue: tiles 0 and 1 in flight, S(0) issued
+      load_k(Lc, 0);
+      load_v(Lc, 0);
+      cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
+      if (Lc.idx < n_items) {
+        load_k(Lc, 1);
+        load_v(Lc, 1);
+        cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
+      }
+      issue_s(Sc, 0);
+      cursor_next(Sc, n_items, stride, n_qt, heads, R, kv_len);
+
+      for (int g = 0; Pc.idx < n_items; ++g) {
+        // invariant: Pc = tile g, Sc = tile g+1, Lc = tile g+2
+        if (Sc.idx < n_items) {
+          issue_s(Sc, g + 1);
+          cursor_next(Sc, n_items, stride, n_qt, heads, R, kv_len);
+          // S(g) has retired (S(g+1) was issued after s_free(g)), so K buffer g&1 can be refilled;
+          // a Q buffer is refilled two items later, when every QK^T of its old item has retired too
+          if (Lc.idx < n_items) load_k(Lc, g + 2);
         }
-        mbar_wait(&v_full[j & 1], (uint32_t)((j >> 1) & 1));
-        mbar_wait(p_full, (uint32_t)(j & 1));        // P(j) in smem, O rescaled if it had to be
-        A6_T(0, 3);   // p_full seen
+        mbar_wait(&v_full[g & 1], (uint32_t)((g >> 1) & 1));
+        mbar_wait(p_full, (uint32_t)(g & 1));        // P(g) in TMEM, O rescaled if it had to be
+        if (Pc.j == 0 && Pc.seq > 0)                 // O of the previous item is in the epilogue's registers
+          mbar_wait(o_free, (uint32_t)((Pc.seq - 1) & 1));
         tc_fence_after();
         {
-          const uint64_t vd = v_desc0 + (uint64_t)(((j & 1) * A6_TILE_BYTES) >> 4);
+          const uint64_t vd = v_desc0 + (uint64_t)(((g & 1) * A6_TILE_BYTES) >> 4);
+          const uint32_t first = (uint32_t)(Pc.j != 0);
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < A6_BN / 16; ++kk) {
+            for (int kk = 0; kk < A6_BN / 16; ++kk)
               tc_mma_ts(tO, tmem_base + A6_P_COL + (uint32_t)(kk * 8), vd + (uint64_t)((kk * 16 * 128) >> 4),
-                        idesc_o, (uint32_t)((j | kk) != 0));
-            }
+                        idesc_o, (kk != 0) ? 1u : first);
             tc_commit(pv_done);
-            A6_T(0, 4);   // PV issued
           }
           __syncwarp();
         }
-        if (j + 2 < n_tiles) {
-          mbar_wait(pv_done, (uint32_t)(j & 1));     // V buffer j&1 is free once PV(j) retired
-          load_tile(sV + (j & 1) * A6_TILE_BYTES, &v_full[j & 1], vcol, row_base + (j + 2) * A6_BN);
+        cursor_next(Pc, n_items, stride, n_qt, heads, R, kv_len);
+        if (Lc.idx < n_items) {
+          mbar_wait(pv_done, (uint32_t)(g & 1));     // V buffer g&1 is free once PV(g) retired
+          load_v(Lc, g + 2);
+          cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
         }
       }
     }
@@ -285,59 +348,93 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
     const uint32_t tP_mine = tmem_base + A6_P_COL + lane_off + (uint32_t)(hf * 32);
     float* x_own = xch + hf * 128 + r;               // + 256 * (tile parity)
     const float* x_peer = xch + (hf ^ 1) * 128 + r;
-    float m_used = 0.f;                              // running max (log2 units) used in exponents
-    float l_sum = 0.f;                               // this warp's half of the row sum
+    int g = 0;                                       // position in the CTA's tile stream
+    int seq = 0;                                     // non-empty items so far
 
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, (uint32_t)(j & 1));
-      A6_T(1, 1);   // s_full seen
-      tc_fence_after();
-      float s[64];
-      tmem_ld_x64(tS_mine, s);
-      tc_wait_ld();
-      tc_fence_before();                               // S(j) is in registers: release the S columns
-      __syncwarp();                                    // for QK^T of tile j+1 right away
-      if (lane == 0) mbar_arrive(s_free);
-      A6_T(1, 2);   // S in registers
-      const int n_valid = klen - j * A6_BN - hf * 64;    // valid keys among this warp's 64 columns
-      if (n_valid < 64) {                                // only the last tile has masked keys
+    Item nxt;
+    if ((int)blockIdx.x < n_items) nxt = make_item(blockIdx.x, n_qt, heads, R, kv_len);
+    for (int idx = blockIdx.x; idx < n_items; idx += stride) {
+      const Item it = nxt;
+      if (idx + stride < n_items) nxt = make_item(idx + stride, n_qt, heads, R, kv_len);  // kv_len load in flight early
+      if (it.n_tiles == 0) {                         // no valid key at all: zeros
+        const int row = it.q0 + r;
+        __nv_bfloat16* out = ctx + ((long long)(it.row_base + row)) * D + it.head * A6_DH + hf * 32;
+        if (row < R) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= n_valid) s[i] = -INFINITY;            // exp2(-inf) = 0 exactly
-      }
-      float m4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) m4[i] = max3(s[i], s[4 + i], s[8 + i]);
-#pragma unroll
-      for (int i = 12; i < 60; i += 8) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) m4[k] = max3(m4[k], s[i + k], s[i + 4 + k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], s[60 + k]);
-      const float mx_own = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
-      // the exchange slots alternate with the tile parity: a warp can only reach its write for tile
-      // j+2 after the pair barrier of tile j+1, which its peer enters after reading the slot of tile j
-      x_own[(j & 1) * 256] = mx_own;
-      pair_barrier(1 + quarter);
-      A6_T(1, 3);   // max + exchange barrier passed
-      const float mx = fmaxf(mx_own, x_peer[(j & 1) * 256]);
-
-      float factor = 1.f;
-      bool need = false;
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        need = mx > m_used + A6_RESCALE_THRESHOLD;
-        if (need) {
-          factor = ex2a(m_used - mx);
-          m_used = mx;
-          l_sum *= factor;
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(0, 0, 0, 0);
         }
-        // PV(j-1) must have retired before P is overwritten or O is rescaled
-        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        continue;
+      }
+      float m_used = 0.f;                            // running max (log2 units) used in exponents
+      float l_sum = 0.f;                             // this warp's half of the row sum
+
+      for (int j = 0; j < it.n_tiles; ++j, ++g) {
+        A6_T(0);
+        mbar_wait(s_full, (uint32_t)(g & 1));
+        A6_T(1);
+#ifdef A6_TRACE
+        if (threadIdx.x == 0 && g < 64) {
+          const int w = blockIdx.x == 5 ? 0 : blockIdx.x == 100 ? 1 : blockIdx.x == 153 ? 2 : blockIdx.x == 290 ? 3 : -1;
+          if (w >= 0) g_tile_t[w][g] = clock64() - t_cta0;
+        }
+#endif
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {           // the peer warp takes the same branch
+        float s[64];
+        tmem_ld_x64(tS_mine, s);
+        tc_wait_ld();
+        tc_fence_before();                           // S(g) is in registers: release the S columns
+        __syncwarp();                                // for QK^T of tile g+1 right away
+        if (lane == 0) mbar_arrive(s_free);
+        if (j == 0 && seq > 0 && threadIdx.x == 0) {   // previous item's output store has left its staging
+          bulk_wait_group_read0();                     // tile (= that item's Q buffer): hand it back to
+          mbar_arrive(stage_free);                     // the producer (it refills it for item seq+1)
+        }
+        A6_T(2);
+        const int n_valid = it.klen - j * A6_BN - hf * 64;   // valid keys among this warp's 64 columns
+        if (n_valid < 64) {                          // only the last tile has masked keys
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= n_valid) s[i] = -INFINITY;      // exp2(-inf) = 0 exactly
+        }
+        float m4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m4[i] = max3(s[i], s[4 + i], s[8 + i]);
+#pragma unroll
+        for (int i = 12; i < 60; i += 8) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m4[k] = max3(m4[k], s[i + k], s[i + 4 + k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], s[60 + k]);
+        const float mx_own = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+        // the exchange slots alternate with the tile parity: a warp can only reach its write for
+        // tile g+2 after the pair barrier of tile g+1, which its peer enters after reading slot g
+        x_own[(g & 1) * 256] = mx_own;
+        pair_barrier(1 + quarter);
+        const float mx = fmaxf(mx_own, x_peer[(g & 1) * 256]);
+        A6_T(3);
+
+        float factor = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          need = mx > m_used + A6_RESCALE_THRESHOLD;
+          if (need) {
+            factor = ex2a(m_used - mx);
+            m_used = mx;
+            l_sum *= factor;
+          }
+        }
+        // PV(g-1) must have retired before P is overwritten or O is rescaled. The wait sits right
+        // before the P store (after the exponentials), except in the rare rescale branch.
+        bool pv_seen = (g == 0);
+        if (__any_sync(0xffffffffu, need)) {         // the peer warp takes the same branch
+          if (!pv_seen) {
+            mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
+            tc_fence_after();
+            pv_seen = true;
+          }
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t o[8];
@@ -349,59 +446,81 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
           }
           tc_wait_st();
         }
-      }
 
-      // p = 2^(s*scale - m): one FFMA + one MUFU per element, 4 partial sums, bf16, 16-byte chunks
-      // into the K-major SW128 layout (this warp's 64 keys = one 128-byte row of P half `hf`).
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_used;
-      {
-        uint32_t pk[32];
+        A6_T(4);
+        // p = 2^(s*scale - m): one FFMA + one MUFU per element, 4 partial sums; P -> TMEM as packed
+        // bf16x2 (this warp's 64 keys = 32 columns of the A operand of P V)
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m_used;
+        {
+          uint32_t pk[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e0 = ex2a(fmaf(s[2 * i], scale_log2, neg_m));
-          const float e1 = ex2a(fmaf(s[2 * i + 1], scale_log2, neg_m));
-          sum4[i & 3] += e0 + e1;
-          pk[i] = pack_bf16x2(e0, e1);
+          for (int i = 0; i < 32; ++i) {
+            const float e0 = ex2a(fmaf(s[2 * i], scale_log2, neg_m));
+            const float e1 = ex2a(fmaf(s[2 * i + 1], scale_log2, neg_m));
+            sum4[i & 3] += e0 + e1;
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          if (!pv_seen) {
+            mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
+            tc_fence_after();
+          }
+          tmem_st_x32(tP_mine, pk);
         }
-        tmem_st_x32(tP_mine, pk);
+        l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        A6_T(5);
+        tc_wait_st();
+        tc_fence_before();                           // P (and a rescaled O) ordered before the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        A6_T(6);
       }
-      l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      tc_wait_st();
-      tc_fence_before();                             // P (and a rescaled O) ordered before the MMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      A6_T(1, 5);   // P stored, arrived
-    }
 
-    // ---- epilogue: O / (l_own + l_peer) -> bf16 -> ctx; this warp writes O columns hf*32..+31
-    const int row = q0 + r;
-    __nv_bfloat16* out = ctx + ((long long)(row_base + row)) * D + head * A6_DH + hf * 32;
-    if (n_tiles > 0) {
-      mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+      // ---- item epilogue: O / (l_own + l_peer) -> bf16 -> ctx; this warp writes O columns hf*32..+31
+      A6_E(0);
+      mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
+      A6_E(1);
       tc_fence_after();
-      float* lx = reinterpret_cast<float*>(smem + A6_OFF_L);   // fp32 [2][128] row-sum exchange
-      lx[hf * 128 + r] = l_sum;
-      pair_barrier(1 + quarter);
-      const float inv = 1.f / (l_sum + lx[(hf ^ 1) * 128 + r]);
       uint32_t o[32];
       tmem_ld_32x32b_x32(tO_mine, o);
+      float* lx = lxb + (seq & 1) * 256;             // row-sum exchange, item-parity buffered
+      lx[hf * 128 + r] = l_sum;
       tc_wait_ld();
-      if (row < R) {
+      tc_fence_before();                             // O is in registers: PV of the next item may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      // The tile leaves through shared memory (128-byte-swizzled rows, both column halves side by
+      // side) and ONE TMA store per item: row-strided 16-byte stores straight from the registers
+      // cost ~2000 cycles per item here. The staging tile is this item's own Q buffer (every QK^T
+      // of the item has retired); the 3-D map clips rows >= R of the last query tile.
+      A6_E(2);
+      pair_barrier(1 + quarter);
+      A6_E(3);
+      const float inv = 1.f / (l_sum + lx[(hf ^ 1) * 128 + r]);
+      uint8_t* stage = sQ + (seq & 1) * A6_TILE_BYTES;
+      const uint32_t o_stage = smem_u32(stage) + (uint32_t)(r * 128);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(out + i * 8) = u;
-        }
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t u0 = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        const uint32_t u1 = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        const uint32_t u2 = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        const uint32_t u3 = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o_stage + (uint32_t)(((hf * 4 + i) ^ (r & 7)) << 4)),
+                     "r"(u0), "r"(u1), "r"(u2), "r"(u3)
+                     : "memory");
       }
-    } else if (row < R) {                            // no valid key at all: zeros
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+      A6_E(4);
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      A6_E(5);
+      if (threadIdx.x == 0) {
+        tma_store_3d(&tmap_out, stage, it.head * A6_DH, it.q0, it.b);
+        bulk_commit_group();
+      }
+      A6_E(6);
+      ++seq;
     }
+    if (threadIdx.x == 0) bulk_wait_group_read0();   // shared memory must outlive the last store's read
   }
 
   tc_fence_before();
@@ -411,13 +530,23 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int R, int h
     tmem_dealloc(tmem_base, A6_TMEM_COLS);
   }
 #ifdef A6_TRACE
-  if (blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 7 && threadIdx.x == 0) {
-    printf("end %lld\n", clock64() - t_start);
-    for (int j = 0; j < 8; ++j)
-      printf("tile %d ctrl: s_free %lld S_issued %lld S_done %lld p_full %lld PV_issued %lld | smax: s_full %lld loaded %lld xchg %lld pvdone %lld arrived %lld\n",
-             j, g_trace[0][j][1], g_trace[0][j][2], g_trace[0][j][5], g_trace[0][j][3], g_trace[0][j][4], g_trace[1][j][1],
-             g_trace[1][j][2], g_trace[1][j][3], g_trace[1][j][4], g_trace[1][j][5]);
+  if ((blockIdx.x == 5 || blockIdx.x == 100 || blockIdx.x == 153 || blockIdx.x == 290) && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("cta %d on sm %u: %lld cycles\n", (int)blockIdx.x, smid, clock64() - t_cta0);
+    if (blockIdx.x == 5) printf("  item 2 epilogue: last arrive %lld pv_done %lld o_free %lld pair %lld staged %lld bar256 %lld stored %lld\n", g_ep[0], g_ep[1], g_ep[2], g_ep[3], g_ep[4], g_ep[5], g_ep[6]);
+    const int w = blockIdx.x == 5 ? 0 : blockIdx.x == 100 ? 1 : blockIdx.x == 153 ? 2 : 3;
+    for (int t = 0; t < 56; t += 8)
+      printf("  cta %d tiles %d..: %lld %lld %lld %lld %lld %lld %lld %lld\n", (int)blockIdx.x, t, g_tile_t[w][t],
+             g_tile_t[w][t + 1], g_tile_t[w][t + 2], g_tile_t[w][t + 3], g_tile_t[w][t + 4], g_tile_t[w][t + 5],
+             g_tile_t[w][t + 6], g_tile_t[w][t + 7]);
   }
+  if (blockIdx.x == 5 && threadIdx.x == 0)
+    for (int t = 0; t < 8; ++t)
+      printf("tile %d: wait_s %lld ld %lld max+xchg %lld pv_wait %lld exp %lld st_wait+arrive %lld | period %lld\n", 20 + t,
+             g_trace[t][1] - g_trace[t][0], g_trace[t][2] - g_trace[t][1], g_trace[t][3] - g_trace[t][2],
+             g_trace[t][4] - g_trace[t][3], g_trace[t][5] - g_trace[t][4], g_trace[t][6] - g_trace[t][5],
+             t ? g_trace[t][0] - g_trace[t - 1][0] : 0ll);
 #endif
 }
 
@@ -429,6 +558,8 @@ int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, con
   const int D = heads * A6_DH;
   CUtensorMap tm;
   W2V_TRY(make_tmap_2d_bf16(&tm, qkv, (uint64_t)3 * D, (uint64_t)B * R, (uint64_t)3 * D, 64, A6_BN));
+  CUtensorMap tm_out;   // [B][R][D]: a box over the end of a window is clipped, not spilled into the next
+  W2V_TRY(make_tmap_3d_bf16(&tm_out, ctx, (uint64_t)D, (uint64_t)R, (uint64_t)B, (uint64_t)D, (uint64_t)R * D, 64, A6_BM));
   const float scale_log2 = scale * 1.4426950408889634f;
   static bool attr = false;
   if (!attr) {
@@ -436,9 +567,15 @@ int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, con
                                         A6_SMEM_BYTES));
     attr = true;
   }
-  dim3 grid((R + A6_BM - 1) / A6_BM, heads, B);
+  const int n_qt = (R + A6_BM - 1) / A6_BM;
+  const long long n_items = (long long)n_qt * heads * B;
+  W2V_REQUIRE(n_items < (1ll << 30), "attention: too many work items");
+  W2V_REQUIRE(B <= A6_MAX_B, "attention: at most %d windows per launch (got %d)", A6_MAX_B, B);
+  const long long slots = 2ll * num_sms();           // persistent: two CTAs per SM
+  const int grid = (int)(n_items < slots ? n_items : slots);
   ProfScope ps(s, "attention_d64");
-  attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, s>>>(tm, R, heads, kv_len, scale_log2, ctx);
+  attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B, kv_len,
+                                                                scale_log2, ctx);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -81,6 +81,29 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return 0;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+  CUtensorMap probe;
+  W2V_TRY(make_tmap_2d_bf16(&probe, base, dim0, dim1, stride1_elems, box0, box1));  // loads the encoder, checks alignment
+  if ((stride2_elems * 2) % 16 != 0) {
+    set_error("tensor map: plane stride %llu not 16-byte aligned", (unsigned long long)stride2_elems);
+    return W2VSEG_ERR_ARG;
+  }
+  cuuint64_t gdim[3] = {dim0, dim1, dim2};
+  cuuint64_t gstride[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return W2VSEG_ERR_CUDA;
+  }
+  return 0;
+}
+
 // ---- profiling -----------------------------------------------------------------------------
 namespace {
 struct ProfRec { std::string name; cudaEvent_t a, b; };
