@@ -1,25 +1,28 @@
-// Fused non-causal attention for head_dim 64 (the 16 x 64 encoder layers): tcgen05 / TMEM / TMA,
-// EIGHT softmax warps per CTA with the S tile split by COLUMNS, each warp keeping its 64 scores
-// in registers (one TMEM read per score, exact row max, no second pass).
+// Fused non-causal attention for head_dim 64 (the 16 x 64 encoder layers): tcgen05 / TMEM / TMA.
+// Persistent CTAs (two per SM) walk work items (window, head, 128-row query tile); the key tiles of
+// all items of a CTA form ONE stream, so the K/V loads and the first QK^T of the next item overlap
+// the tail of the current one.
 //
-// Why (profiles/attention_r01b.md): ncu on the 4-warp kernel (attention_tc.cu, thread = whole
-// 128-key row, two TMEM passes) shows issue slots 49 % and MUFU 50 % busy with the warps stalled on
-// the long scoreboard (tcgen05.ld + mbarrier polls): with 2 softmax warps per scheduler nothing
-// hides those latencies. A single warp only sustains ~44 B/clk of tcgen05.ld (16 warps reach
-// 477 B/clk per SM, experiments/tmem_ld_bw.cu), so the per-warp chain, not the TMEM, is the limit.
-// Here two warps share each TMEM lane quarter: warp w (0..3) owns key columns 0..63 of the tile,
-// warp w+4 columns 64..127 of the SAME 32 query rows. That halves every per-warp latency chain,
-// doubles the warps per scheduler (2 CTAs per SM -> 16 softmax warps) and lets the 64 scores stay
-// in registers between the max and the exponentials. The two warps agree on the row max through a
-// small fp32 exchange in shared memory and one
-// 64-thread named barrier per tile; row sums stay per-warp until the end. P goes to TMEM as packed
-// bf16x2 (64 columns) and is the A operand of a TS-form MMA: shared memory only carries Q, K and V
-// (with P in shared memory the tile needs ~1150 cycles of shared-memory bandwidth per SM, more
-// than the 1024 cycles of MUFU work: measured 121 -> 113 us).
+//   warps 0..7  softmax. Warp w owns 16 query rows (TMEM lanes 32(w%4) + 16(w/4) ..) x all 128 keys
+//               of the tile in the 16x256b TMEM shape: a row lives in one quad, so the row max / sum
+//               are two shuffles (no cross-warp exchange) and the 64 scores of a thread stay in
+//               registers between the max and the exponentials (ONE TMEM read per score, exact
+//               max, no second pass). P goes back to TMEM as packed bf16x2 (tcgen05.st 16x128b).
+//   warp 8      TMA producer (Q double-buffered per item, K/V per tile) + MMA issuer; the whole warp
+//               runs the control flow (uniform registers), one elected lane issues.
+//   TMEM        S 128 columns fp32 | O 64 columns fp32 | P 64 columns bf16x2 (A operand of the
+//               TS-form P V MMA; V is consumed in place as an MN-major B operand)
+//   output      O / l -> bf16 -> the item's own (retired) Q buffer -> one TMA store per item
+//               through a [B][R][D] map that clips the rows past the end of a window.
 //
-//   warps 0..7  softmax (thread = one query row x 64 keys), P -> TMEM (tcgen05.st 32x32b)
-//   warp 8      TMA producer (Q once, K/V double-buffered) + MMA issuer (warp-uniform, elect_one)
-//   TMEM        S 128 columns fp32 | O 64 columns fp32 | P 64 columns bf16x2   (two CTAs per SM)
+// What the measurements said (profiles/attention_experiments_r01.md, section "session 2"):
+//  * tcgen05.ld: one warp sustains only ~44 B/clk, 16 warps 477 B/clk per SM -> 8 softmax warps.
+//  * P in shared memory costs ~1150 cycles of smem bandwidth per 128x128 tile per SM (more than the
+//    1024 cycles of MUFU work) -> P in TMEM: 121 -> 113 us.
+//  * S released right after the TMEM load, PV(g-1) awaited only right before the P store: 109 us.
+//  * row-strided 16-byte output stores from registers cost ~2000 cycles per item -> TMA store;
+//    the per-item global load of the key length ~2000 more -> key lengths in shared memory.
+//  * persistent tile stream + the above: 106 us (B=14, R=1000; the 4-warp two-pass kernel: 124 us).
 // Rescaling is lazy (FlashAttention-4): the exponent's running max only advances when a tile max
 // exceeds it by more than 2^8. Replaces Wav2Vec2Attention's softmax(QK^T*scale + key mask) V
 // (HF:500-549).
@@ -40,10 +43,8 @@ constexpr int A6_OFF_Q = 0;                            // 2 buffers (item parity
 constexpr int A6_OFF_K = A6_OFF_Q + 2 * A6_TILE_BYTES; // 2 buffers (tile parity)
 constexpr int A6_OFF_V = A6_OFF_K + 2 * A6_TILE_BYTES; // 2 buffers
 constexpr int A6_OFF_BAR = A6_OFF_V + 2 * A6_TILE_BYTES;   // 12 mbarriers + TMEM slot
-constexpr int A6_OFF_X = A6_OFF_BAR + 128;             // fp32 [2 tile parities][2 halves][128] row max
-constexpr int A6_OFF_L = A6_OFF_X + 2048;              // fp32 [2 item parities][2 halves][128] row sums
 // the kernel traps if the dynamic smem base is not 1024-byte aligned (no alignment slack)
-constexpr int A6_OFF_KLEN = A6_OFF_L + 2048;           // int32 [A6_MAX_B] clamped key lengths
+constexpr int A6_OFF_KLEN = A6_OFF_BAR + 128;          // int32 [A6_MAX_B] clamped key lengths
 constexpr int A6_MAX_B = 1024;
 constexpr int A6_SMEM_BYTES = A6_OFF_KLEN + A6_MAX_B * 4;
 constexpr int A6_TMEM_COLS = 256;
@@ -61,9 +62,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ void pair_barrier(int id) {   // the two warps of one lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
-}
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -73,57 +71,56 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t l
   d |= (uint64_t)2 << 61;
   return d;
 }
-// 32 lanes x 64 consecutive fp32 columns in one instruction (thread i = TMEM lane base + i)
-__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, float (&r)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
-        "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]),
-        "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]),
-        "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]),
-        "=f"(r[29]), "=f"(r[30]), "=f"(r[31]), "=f"(r[32]), "=f"(r[33]), "=f"(r[34]), "=f"(r[35]),
-        "=f"(r[36]), "=f"(r[37]), "=f"(r[38]), "=f"(r[39]), "=f"(r[40]), "=f"(r[41]), "=f"(r[42]),
-        "=f"(r[43]), "=f"(r[44]), "=f"(r[45]), "=f"(r[46]), "=f"(r[47]), "=f"(r[48]), "=f"(r[49]),
-        "=f"(r[50]), "=f"(r[51]), "=f"(r[52]), "=f"(r[53]), "=f"(r[54]), "=f"(r[55]), "=f"(r[56]),
-        "=f"(r[57]), "=f"(r[58]), "=f"(r[59]), "=f"(r[60]), "=f"(r[61]), "=f"(r[62]), "=f"(r[63])
-      : "r"(taddr)
-      : "memory");
+// TMEM access in the 16-lane shapes: a warp owns 16 query rows x all columns; thread t holds rows
+// t/4 and t/4+8 and, of every 8-column group k, columns 8k + 2(t%4) and +1:
+//   16x256b register 4k + e : row t/4 + 8(e>>1), column 8k + 2(t%4) + (e&1)
+//   16x128b register 2k + e : row t/4 + 8e,      32-bit column 4k + t%4   (= the packed pair above)
+// so a row lives in one quad (max / sum by two shuffles, no cross-warp exchange) and the bf16x2
+// pairs a thread computes are exactly the P words it stores.
+__device__ __forceinline__ void tmem_ld_16x256b_x16(uint32_t taddr, float (&r)[64]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31]), "=f"(r[32]), "=f"(r[33]), "=f"(r[34]), "=f"(r[35]), "=f"(r[36]), "=f"(r[37]), "=f"(r[38]), "=f"(r[39]), "=f"(r[40]), "=f"(r[41]), "=f"(r[42]), "=f"(r[43]), "=f"(r[44]), "=f"(r[45]), "=f"(r[46]), "=f"(r[47]), "=f"(r[48]), "=f"(r[49]), "=f"(r[50]), "=f"(r[51]), "=f"(r[52]), "=f"(r[53]), "=f"(r[54]), "=f"(r[55]), "=f"(r[56]), "=f"(r[57]), "=f"(r[58]), "=f"(r[59]), "=f"(r[60]), "=f"(r[61]), "=f"(r[62]), "=f"(r[63])
+               : "r"(taddr)
+               : "memory");
 }
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
-        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
-        "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr)
+               : "memory");
 }
-// 8-column TMEM load / store: the (rare) rescale of O runs in small chunks so that it does not
-// push the 64 live scores out of the register file
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :
                : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-
+__device__ __forceinline__ void tmem_st_16x128b_x16(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+               : "memory");
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 
 // -DA6_TRACE: clock64 timeline of softmax warp 0 of CTA 5 for stream tiles 16..23, printed at exit
 #ifdef A6_TRACE
+#ifndef A6_TRACE_CTA
+#define A6_TRACE_CTA 5
+#endif
 __device__ long long g_trace[8][8];
 __device__ long long g_tile_t[4][64];
 __device__ long long g_ep[8];
@@ -131,7 +128,7 @@ __device__ long long g_ep[8];
    // per-tile s_full-seen stamps of 4 sample CTAs
 #define A6_T(ev)                                                                                   \
   do {                                                                                             \
-    if (blockIdx.x == 5 && threadIdx.x == 0 && g >= 20 && g < 28) g_trace[g - 20][ev] = clock64(); \
+    if (blockIdx.x == A6_TRACE_CTA && threadIdx.x == 0 && g >= 20 && g < 28) g_trace[g - 20][ev] = clock64(); \
   } while (0)
 #else
 #define A6_T(ev) do {} while (0)
@@ -204,8 +201,6 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   uint64_t* o_free = bars + 10;
   uint64_t* stage_free = bars + 11;   // completion k: the output store of item k has read its staging tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xch = reinterpret_cast<float*>(smem + A6_OFF_X);   // [2][2][128]
-  float* lxb = reinterpret_cast<float*>(smem + A6_OFF_L);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * A6_DH;
@@ -338,16 +333,16 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax: thread = row x 64 keys
+    // ------------------------------------------------------------ softmax: warp = 16 rows x 128 keys
     const int quarter = warp & 3;                    // TMEM lane quarter (hardware: warp id % 4)
-    const int hf = warp >> 2;                        // key-column half of the tile
-    const int r = quarter * 32 + lane;               // query row in the tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS_mine = tS + lane_off + (uint32_t)(hf * 64);
-    const uint32_t tO_mine = tO + lane_off + (uint32_t)(hf * 32);
-    const uint32_t tP_mine = tmem_base + A6_P_COL + lane_off + (uint32_t)(hf * 32);
-    float* x_own = xch + hf * 128 + r;               // + 256 * (tile parity)
-    const float* x_peer = xch + (hf ^ 1) * 128 + r;
+    const int hf = warp >> 2;                        // which 16 rows of the quarter
+    const int row_lo = quarter * 32 + hf * 16 + (lane >> 2);   // this thread's query rows in the tile:
+    const int row_hi = row_lo + 8;                              // row_lo and row_lo + 8
+    const int cpair = 2 * (lane & 3);                // its columns: 8k + cpair, 8k + cpair + 1
+    const uint32_t lane_off = (uint32_t)(quarter * 32 + hf * 16) << 16;
+    const uint32_t tS_mine = tS + lane_off;
+    const uint32_t tO_mine = tO + lane_off;
+    const uint32_t tP_mine = tmem_base + A6_P_COL + lane_off;
     int g = 0;                                       // position in the CTA's tile stream
     int seq = 0;                                     // non-empty items so far
 
@@ -355,32 +350,27 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     if ((int)blockIdx.x < n_items) nxt = make_item(blockIdx.x, n_qt, heads, R, kv_len);
     for (int idx = blockIdx.x; idx < n_items; idx += stride) {
       const Item it = nxt;
-      if (idx + stride < n_items) nxt = make_item(idx + stride, n_qt, heads, R, kv_len);  // kv_len load in flight early
+      if (idx + stride < n_items) nxt = make_item(idx + stride, n_qt, heads, R, kv_len);
       if (it.n_tiles == 0) {                         // no valid key at all: zeros
+        const int r = threadIdx.x >> 1, h2 = threadIdx.x & 1;   // 256 threads: row x 64-byte half
         const int row = it.q0 + r;
-        __nv_bfloat16* out = ctx + ((long long)(it.row_base + row)) * D + it.head * A6_DH + hf * 32;
+        __nv_bfloat16* out = ctx + ((long long)(it.row_base + row)) * D + it.head * A6_DH + h2 * 32;
         if (row < R) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
-      float m_used = 0.f;                            // running max (log2 units) used in exponents
-      float l_sum = 0.f;                             // this warp's half of the row sum
+      float m_lo = 0.f, m_hi = 0.f;                  // running max (log2 units) used in exponents
+      float l_lo = 0.f, l_hi = 0.f;                  // this thread's part of the two row sums
 
       for (int j = 0; j < it.n_tiles; ++j, ++g) {
         A6_T(0);
         mbar_wait(s_full, (uint32_t)(g & 1));
         A6_T(1);
-#ifdef A6_TRACE
-        if (threadIdx.x == 0 && g < 64) {
-          const int w = blockIdx.x == 5 ? 0 : blockIdx.x == 100 ? 1 : blockIdx.x == 153 ? 2 : blockIdx.x == 290 ? 3 : -1;
-          if (w >= 0) g_tile_t[w][g] = clock64() - t_cta0;
-        }
-#endif
         tc_fence_after();
-        float s[64];
-        tmem_ld_x64(tS_mine, s);
+        float s[64];                                 // s[4k+e]: row (e>>1 ? hi : lo), column 8k+cpair+(e&1)
+        tmem_ld_16x256b_x16(tS_mine, s);
         tc_wait_ld();
         tc_fence_before();                           // S(g) is in registers: release the S columns
         __syncwarp();                                // for QK^T of tile g+1 right away
@@ -390,84 +380,83 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
           mbar_arrive(stage_free);                     // the producer (it refills it for item seq+1)
         }
         A6_T(2);
-        const int n_valid = it.klen - j * A6_BN - hf * 64;   // valid keys among this warp's 64 columns
-        if (n_valid < 64) {                          // only the last tile has masked keys
+        const int n_valid = it.klen - j * A6_BN;     // >= 1; >= 128 except for the last tile
+        if (n_valid < A6_BN) {                       // masked keys -> -inf (exp2 gives exactly 0)
 #pragma unroll
           for (int i = 0; i < 64; ++i)
-            if (i >= n_valid) s[i] = -INFINITY;      // exp2(-inf) = 0 exactly
+            if ((i >> 2) * 8 + cpair + (i & 1) >= n_valid) s[i] = -INFINITY;
         }
-        float m4[4];
+        float a0 = max3(s[0], s[1], s[4]), a1 = max3(s[5], s[8], s[9]);
+        float b0 = max3(s[2], s[3], s[6]), b1 = max3(s[7], s[10], s[11]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m4[i] = max3(s[i], s[4 + i], s[8 + i]);
-#pragma unroll
-        for (int i = 12; i < 60; i += 8) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) m4[k] = max3(m4[k], s[i + k], s[i + 4 + k]);
+        for (int k = 3; k < 15; k += 2) {
+          a0 = max3(a0, s[4 * k], s[4 * k + 1]);
+          a1 = max3(a1, s[4 * k + 4], s[4 * k + 5]);
+          b0 = max3(b0, s[4 * k + 2], s[4 * k + 3]);
+          b1 = max3(b1, s[4 * k + 6], s[4 * k + 7]);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) m4[k] = fmaxf(m4[k], s[60 + k]);
-        const float mx_own = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
-        // the exchange slots alternate with the tile parity: a warp can only reach its write for
-        // tile g+2 after the pair barrier of tile g+1, which its peer enters after reading slot g
-        x_own[(g & 1) * 256] = mx_own;
-        pair_barrier(1 + quarter);
-        const float mx = fmaxf(mx_own, x_peer[(g & 1) * 256]);
+        a0 = max3(a0, s[60], s[61]);
+        b0 = max3(b0, s[62], s[63]);
+        const float mx_lo = quad_max(fmaxf(a0, a1)) * scale_log2;
+        const float mx_hi = quad_max(fmaxf(b0, b1)) * scale_log2;
         A6_T(3);
 
-        float factor = 1.f;
+        float f_lo = 1.f, f_hi = 1.f;
         bool need = false;
         if (j == 0) {
-          m_used = mx;
+          m_lo = mx_lo;
+          m_hi = mx_hi;
         } else {
-          need = mx > m_used + A6_RESCALE_THRESHOLD;
-          if (need) {
-            factor = ex2a(m_used - mx);
-            m_used = mx;
-            l_sum *= factor;
-          }
+          if (mx_lo > m_lo + A6_RESCALE_THRESHOLD) { f_lo = ex2a(m_lo - mx_lo); m_lo = mx_lo; l_lo *= f_lo; need = true; }
+          if (mx_hi > m_hi + A6_RESCALE_THRESHOLD) { f_hi = ex2a(m_hi - mx_hi); m_hi = mx_hi; l_hi *= f_hi; need = true; }
         }
         // PV(g-1) must have retired before P is overwritten or O is rescaled. The wait sits right
         // before the P store (after the exponentials), except in the rare rescale branch.
         bool pv_seen = (g == 0);
-        if (__any_sync(0xffffffffu, need)) {         // the peer warp takes the same branch
+        if (__any_sync(0xffffffffu, need)) {
           if (!pv_seen) {
             mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
             tc_fence_after();
             pv_seen = true;
           }
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c) {              // 16 columns at a time: keeps the scores in registers
             uint32_t o[8];
-            tmem_ld_x8(tO_mine + (uint32_t)(c * 8), o);
+            tmem_ld_16x256b_x2(tO_mine + (uint32_t)(c * 16), o);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st_x8(tO_mine + (uint32_t)(c * 8), o);
+            for (int i = 0; i < 8; ++i)
+              o[i] = __float_as_uint(__uint_as_float(o[i]) * ((i & 2) ? f_hi : f_lo));
+            tmem_st_16x256b_x2(tO_mine + (uint32_t)(c * 16), o);
           }
           tc_wait_st();
         }
 
         A6_T(4);
-        // p = 2^(s*scale - m): one FFMA + one MUFU per element, 4 partial sums; P -> TMEM as packed
-        // bf16x2 (this warp's 64 keys = 32 columns of the A operand of P V)
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-        const float neg_m = -m_used;
+        // p = 2^(s*scale - m): one FFMA + one MUFU per element; P -> TMEM as packed bf16x2, the A
+        // operand of P V (pk[2k+e]: row lo/hi, packed column 4k + t%4)
+        float sl0 = 0.f, sl1 = 0.f, sh0 = 0.f, sh1 = 0.f;
+        const float nm_lo = -m_lo, nm_hi = -m_hi;
         {
           uint32_t pk[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e0 = ex2a(fmaf(s[2 * i], scale_log2, neg_m));
-            const float e1 = ex2a(fmaf(s[2 * i + 1], scale_log2, neg_m));
-            sum4[i & 3] += e0 + e1;
-            pk[i] = pack_bf16x2(e0, e1);
+          for (int k = 0; k < 16; ++k) {
+            const float e0 = ex2a(fmaf(s[4 * k + 0], scale_log2, nm_lo));
+            const float e1 = ex2a(fmaf(s[4 * k + 1], scale_log2, nm_lo));
+            const float e2 = ex2a(fmaf(s[4 * k + 2], scale_log2, nm_hi));
+            const float e3 = ex2a(fmaf(s[4 * k + 3], scale_log2, nm_hi));
+            sl0 += e0; sl1 += e1; sh0 += e2; sh1 += e3;
+            pk[2 * k + 0] = pack_bf16x2(e0, e1);
+            pk[2 * k + 1] = pack_bf16x2(e2, e3);
           }
           if (!pv_seen) {
             mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
             tc_fence_after();
           }
-          tmem_st_x32(tP_mine, pk);
+          tmem_st_16x128b_x16(tP_mine, pk);
         }
-        l_sum += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        l_lo += sl0 + sl1;
+        l_hi += sh0 + sh1;
         A6_T(5);
         tc_wait_st();
         tc_fence_before();                           // P (and a rescaled O) ordered before the MMA
@@ -476,48 +465,37 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         A6_T(6);
       }
 
-      // ---- item epilogue: O / (l_own + l_peer) -> bf16 -> ctx; this warp writes O columns hf*32..+31
-      A6_E(0);
+      // ---- item epilogue: O / l -> bf16 -> ctx
       mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
-      A6_E(1);
       tc_fence_after();
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tO_mine, o);
-      float* lx = lxb + (seq & 1) * 256;             // row-sum exchange, item-parity buffered
-      lx[hf * 128 + r] = l_sum;
+      tmem_ld_16x256b_x8(tO_mine, o);
+      const float inv_lo = 1.f / quad_sum(l_lo);
+      const float inv_hi = 1.f / quad_sum(l_hi);
       tc_wait_ld();
       tc_fence_before();                             // O is in registers: PV of the next item may overwrite it
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
-      // The tile leaves through shared memory (128-byte-swizzled rows, both column halves side by
-      // side) and ONE TMA store per item: row-strided 16-byte stores straight from the registers
-      // cost ~2000 cycles per item here. The staging tile is this item's own Q buffer (every QK^T
-      // of the item has retired); the 3-D map clips rows >= R of the last query tile.
-      A6_E(2);
-      pair_barrier(1 + quarter);
-      A6_E(3);
-      const float inv = 1.f / (l_sum + lx[(hf ^ 1) * 128 + r]);
+      // The tile leaves through shared memory (128-byte-swizzled rows) and ONE TMA store per item:
+      // row-strided stores straight from the registers cost ~2000 cycles per item here. The staging
+      // tile is this item's own Q buffer (every QK^T of the item has retired); the 3-D map clips
+      // rows >= R of the last query tile.
       uint8_t* stage = sQ + (seq & 1) * A6_TILE_BYTES;
-      const uint32_t o_stage = smem_u32(stage) + (uint32_t)(r * 128);
+      const uint32_t st_lo = smem_u32(stage) + (uint32_t)(row_lo * 128 + cpair * 2);
+      const uint32_t st_hi = smem_u32(stage) + (uint32_t)(row_hi * 128 + cpair * 2);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t u0 = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-        const uint32_t u1 = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-        const uint32_t u2 = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-        const uint32_t u3 = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o_stage + (uint32_t)(((hf * 4 + i) ^ (r & 7)) << 4)),
-                     "r"(u0), "r"(u1), "r"(u2), "r"(u3)
-                     : "memory");
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t v0 = pack_bf16x2(__uint_as_float(o[4 * k + 0]) * inv_lo, __uint_as_float(o[4 * k + 1]) * inv_lo);
+        const uint32_t v1 = pack_bf16x2(__uint_as_float(o[4 * k + 2]) * inv_hi, __uint_as_float(o[4 * k + 3]) * inv_hi);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_lo + (uint32_t)((k ^ (row_lo & 7)) << 4)), "r"(v0) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_hi + (uint32_t)((k ^ (row_hi & 7)) << 4)), "r"(v1) : "memory");
       }
       fence_proxy_async_smem();
-      A6_E(4);
       asm volatile("bar.sync 5, 256;" ::: "memory");
-      A6_E(5);
       if (threadIdx.x == 0) {
         tma_store_3d(&tmap_out, stage, it.head * A6_DH, it.q0, it.b);
         bulk_commit_group();
       }
-      A6_E(6);
       ++seq;
     }
     if (threadIdx.x == 0) bulk_wait_group_read0();   // shared memory must outlive the last store's read
@@ -541,9 +519,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
              g_tile_t[w][t + 1], g_tile_t[w][t + 2], g_tile_t[w][t + 3], g_tile_t[w][t + 4], g_tile_t[w][t + 5],
              g_tile_t[w][t + 6], g_tile_t[w][t + 7]);
   }
-  if (blockIdx.x == 5 && threadIdx.x == 0)
+  if (blockIdx.x == A6_TRACE_CTA && threadIdx.x == 0)
     for (int t = 0; t < 8; ++t)
-      printf("tile %d: wait_s %lld ld %lld max+xchg %lld pv_wait %lld exp %lld st_wait+arrive %lld | period %lld\n", 20 + t,
+      printf("tile %d: wait_s %lld ld %lld max %lld pv_wait %lld exp %lld st_wait+arrive %lld | period %lld\n", 20 + t,
              g_trace[t][1] - g_trace[t][0], g_trace[t][2] - g_trace[t][1], g_trace[t][3] - g_trace[t][2],
              g_trace[t][4] - g_trace[t][3], g_trace[t][5] - g_trace[t][4], g_trace[t][6] - g_trace[t][5],
              t ? g_trace[t][0] - g_trace[t - 1][0] : 0ll);
