@@ -99,18 +99,23 @@ __global__ void window_stats_final_kernel(const double2* __restrict__ partial,
 
 // =============================================================================================
 // conv layer 0 + LayerNorm(512) + GELU   (HF:281-299, Wav2Vec2LayerNormConvLayer with Cin = 1)
-// one warp per output frame; lane owns channels q*128 + lane*4 + e  (q, e in 0..3)
+// A warp computes FOUR output frames at a time; lane owns channels q*128 + lane*4 + e (q, e in
+// 0..3) of each. The tap weights come from shared memory once per four frames: with one frame per
+// pass the 40 LDS.128 per frame (20 KB per warp) made the kernel shared-memory-bandwidth-bound
+// (~160 cycles per frame per SM, 0.5 of its 0.84 ms at batch 14).
 // =============================================================================================
 constexpr int C0_ROWS = 128;   // frames per block
 constexpr int C0_THREADS = 256;
+constexpr int C0_F = 4;        // frames per warp pass
 
-__global__ void __launch_bounds__(C0_THREADS)
+__global__ void __launch_bounds__(C0_THREADS, 2)
 conv0_ln_gelu_kernel(const float* __restrict__ audio, long long audio_stride,
                      const int* __restrict__ sample_len, const float2* __restrict__ stats,
                      const float* __restrict__ w_t, const float* __restrict__ bias,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      __nv_bfloat16* __restrict__ out, int R0) {
   __shared__ float4 w_s[10 * 128];
+  __shared__ float4 p_s[3 * 128];            // bias | gamma | beta, same channel order as w_s rows
   __shared__ float x_s[C0_ROWS * 5 + 8];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * C0_ROWS;
@@ -120,6 +125,11 @@ conv0_ln_gelu_kernel(const float* __restrict__ audio, long long audio_stride,
 
   for (int i = threadIdx.x; i < 10 * 128; i += C0_THREADS)
     w_s[i] = reinterpret_cast<const float4*>(w_t)[i];
+  for (int i = threadIdx.x; i < 128; i += C0_THREADS) {
+    p_s[i] = reinterpret_cast<const float4*>(bias)[i];
+    p_s[128 + i] = reinterpret_cast<const float4*>(gamma)[i];
+    p_s[256 + i] = reinterpret_cast<const float4*>(beta)[i];
+  }
   for (int i = threadIdx.x; i < C0_ROWS * 5 + 5; i += C0_THREADS) {
     const long long sidx = (long long)t0 * 5 + i;
     x_s[i] = (sidx < len) ? (x[sidx] - st.x) * st.y : 0.f;
@@ -127,57 +137,71 @@ conv0_ln_gelu_kernel(const float* __restrict__ audio, long long audio_stride,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float bi[16], ga[16], be[16];
+  for (int tl = warp * C0_F; tl < C0_ROWS; tl += (C0_THREADS / 32) * C0_F) {
+    if (t0 + tl >= R0) break;
+    float acc[C0_F][16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 v0 = reinterpret_cast<const float4*>(bias)[q * 32 + lane];
-    const float4 v1 = reinterpret_cast<const float4*>(gamma)[q * 32 + lane];
-    const float4 v2 = reinterpret_cast<const float4*>(beta)[q * 32 + lane];
-    bi[4 * q] = v0.x; bi[4 * q + 1] = v0.y; bi[4 * q + 2] = v0.z; bi[4 * q + 3] = v0.w;
-    ga[4 * q] = v1.x; ga[4 * q + 1] = v1.y; ga[4 * q + 2] = v1.z; ga[4 * q + 3] = v1.w;
-    be[4 * q] = v2.x; be[4 * q + 1] = v2.y; be[4 * q + 2] = v2.z; be[4 * q + 3] = v2.w;
-  }
-
-  for (int tl = warp; tl < C0_ROWS; tl += C0_THREADS / 32) {
-    const int t = t0 + tl;
-    if (t >= R0) break;
-    float acc[16];
+    for (int q = 0; q < 4; ++q) {
+      const float4 bi = p_s[q * 32 + lane];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = bi[c];
-#pragma unroll
+      for (int f = 0; f < C0_F; ++f) {
+        acc[f][4 * q + 0] = bi.x; acc[f][4 * q + 1] = bi.y; acc[f][4 * q + 2] = bi.z; acc[f][4 * q + 3] = bi.w;
+      }
+    }
+#pragma unroll 1   // (unrolled, ptxas hoists all 40 weight vectors out of the frame loop: 255 registers)
     for (int j = 0; j < 10; ++j) {
-      const float xv = x_s[tl * 5 + j];
+      float xv[C0_F];
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f) xv[f] = x_s[(tl + f) * 5 + j];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 w = w_s[j * 128 + q * 32 + lane];
-        acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
+#pragma unroll
+        for (int f = 0; f < C0_F; ++f) {
+          acc[f][4 * q + 0] = fmaf(xv[f], w.x, acc[f][4 * q + 0]);
+          acc[f][4 * q + 1] = fmaf(xv[f], w.y, acc[f][4 * q + 1]);
+          acc[f][4 * q + 2] = fmaf(xv[f], w.z, acc[f][4 * q + 2]);
+          acc[f][4 * q + 3] = fmaf(xv[f], w.w, acc[f][4 * q + 3]);
+        }
       }
     }
-    float s = 0.f;
+    // LayerNorm statistics per frame (two-pass over the registers, as torch does)
+    float mean[C0_F], rstd[C0_F];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) s += acc[c];
-    const float mean = warp_sum(s) * (1.f / 512.f);
-    float qv = 0.f;
+    for (int f = 0; f < C0_F; ++f) {
+      float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float d = acc[c] - mean;
-      qv = fmaf(d, d, qv);
+      for (int c = 0; c < 16; ++c) s += acc[f][c];
+      mean[f] = warp_sum(s) * (1.f / 512.f);
     }
-    const float rstd = rsqrtf(warp_sum(qv) * (1.f / 512.f) + eps);
-    __nv_bfloat16* o = out + ((long long)b * R0 + t) * 512;
+#pragma unroll
+    for (int f = 0; f < C0_F; ++f) {
+      float qv = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float d = acc[f][c] - mean[f];
+        qv = fmaf(d, d, qv);
+      }
+      rstd[f] = rsqrtf(warp_sum(qv) * (1.f / 512.f) + eps);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float y[4];
+      const float4 ga = p_s[128 + q * 32 + lane];
+      const float4 be = p_s[256 + q * 32 + lane];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        y[e] = gelu_erf(fmaf((acc[4 * q + e] - mean) * rstd, ga[4 * q + e], be[4 * q + e]));
-      uint2 u;
-      u.x = pack_bf16x2(y[0], y[1]);
-      u.y = pack_bf16x2(y[2], y[3]);
-      reinterpret_cast<uint2*>(o)[q * 32 + lane] = u;
+      for (int f = 0; f < C0_F; ++f) {
+        if (t0 + tl + f < R0) {
+          const float a = rstd[f], m = -mean[f] * rstd[f];   // (v - mean) * rstd = fma(v, a, m)
+          const float y0 = gelu_erf(fmaf(fmaf(acc[f][4 * q + 0], a, m), ga.x, be.x));
+          const float y1 = gelu_erf(fmaf(fmaf(acc[f][4 * q + 1], a, m), ga.y, be.y));
+          const float y2 = gelu_erf(fmaf(fmaf(acc[f][4 * q + 2], a, m), ga.z, be.z));
+          const float y3 = gelu_erf(fmaf(fmaf(acc[f][4 * q + 3], a, m), ga.w, be.w));
+          uint2 u;
+          u.x = pack_bf16x2(y0, y1);
+          u.y = pack_bf16x2(y2, y3);
+          reinterpret_cast<uint2*>(out + ((long long)b * R0 + t0 + tl + f) * 512)[q * 32 + lane] = u;
+        }
+      }
     }
   }
 }
