@@ -192,6 +192,13 @@ int32_t w2vseg_gemm(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N
 int32_t w2vseg_conv_gemm(const void* x_bf16, int64_t rows_out, int32_t C, int32_t kw,
                          int32_t stride, const void* W_bf16, int32_t N, const float* bias,
                          void* out_bf16, void* stream);
+/* Grouped positional convolution (HF:326-379 + HF:764-765) on a zero-padded channels-last input:
+ *   h[b*R + t, o] += gelu(bias[o] + sum_{j<taps, i<64} W[o, j*64 + i] * zpad[b*(R+2*halo) + t + j, (o/64)*64 + i])
+ * zpad bf16 [B*(R+2*halo)+2*halo, D] (halo = taps/2 zero rows around every window), W bf16 [D, taps*64],
+ * h fp32 [B*R, D] updated in place. impl 0: the forward pass's resident-A kernel (posconv_tc.cu),
+ * impl 1: the generic shifted-row GEMM (gemm_tc.cu, a_mode 1) kept as a second implementation. */
+int32_t w2vseg_posconv(const void* zpad_bf16, const void* W_bf16, const float* bias, int32_t B,
+                       int32_t R, int32_t D, int32_t taps, float* h, int32_t impl, void* stream);
 /* LayerNorm over the last dim (C = 512 or 1024). in: fp32 or bf16; out: bf16; act 0/1 (GELU). */
 int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C,
                          const float* gamma, const float* beta, float eps, int32_t act,

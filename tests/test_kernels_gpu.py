@@ -123,6 +123,34 @@ def test_conv_as_implicit_gemm(lib, kw, rows_out):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,R,D,taps", [(2, 300, 1024, 128), (3, 129, 128, 16), (1, 1000, 256, 128)])
+def test_posconv(lib, B, R, D, taps, impl):
+    """grouped positional conv + GELU + residual (HF:326-379, 764-765): the resident-A kernel of the
+    forward pass (impl 0) and the generic shifted-row GEMM (impl 1) against torch conv1d"""
+    from wav2vecsegmenter_b200 import _native as n
+
+    halo, G = taps // 2, D // 64
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + R + taps)
+    x = torch.randn(B, R, D, device="cuda", generator=g).bfloat16()                 # conv input
+    w = (torch.randn(D, 64, taps, device="cuda", generator=g) / math.sqrt(64 * taps)).bfloat16()  # [O, I/g, J]
+    bias = torch.randn(D, device="cuda", generator=g) * 0.1
+    h0 = torch.randn(B * R, D, device="cuda", generator=g)
+    zpad = torch.zeros(B * (R + 2 * halo) + 2 * halo, D, device="cuda", dtype=torch.bfloat16)
+    for b in range(B):
+        zpad[b * (R + 2 * halo) + halo: b * (R + 2 * halo) + halo + R] = x[b]
+    wp = w.permute(0, 2, 1).contiguous().view(D, taps * 64)                          # K index = j*64 + i
+    h = h0.clone()
+    n.check(lib.w2vseg_posconv(n.ptr(zpad), n.ptr(wp), n.ptr(bias), B, R, D, taps, n.ptr(h), impl,
+                               n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    y = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=halo, groups=G)
+    y = y[:, :, :R].transpose(1, 2).reshape(B * R, D)                                # SamePad drops the last frame
+    ref = h0 + torch.nn.functional.gelu(y)
+    err = (h - ref).abs().max().item()
+    assert err < 5e-3, f"max abs err {err}"
+
+
 @pytest.mark.parametrize("C,in_f32,act", [(1024, True, 0), (512, False, 0), (512, False, 1), (512, True, 0)])
 def test_layernorm(lib, C, in_f32, act):
     from wav2vecsegmenter_b200 import _native as n

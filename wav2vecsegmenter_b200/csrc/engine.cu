@@ -272,6 +272,21 @@ GemmProblem linear(const bf16* A, int64_t M, int K, const bf16* W, int N, const 
   return g;
 }
 
+// grouped positional conv over the zero-padded input (halo = taps/2 rows around every window), h += gelu(..)
+static GemmProblem posconv_problem(const bf16* zpad, const bf16* W, const float* bias, int B, int R, int D,
+                                   int taps, float* h) {
+  const int halo = taps / 2;
+  GemmProblem g = {};
+  g.A = zpad; g.a_rows = (int64_t)B * (R + 2 * halo) + 2 * halo; g.a_row_stride = D; g.a_cols = D;
+  g.W = W; g.N = D; g.K = 64 * taps;
+  g.num_groups = B; g.rows_per_group = R; g.a_group_rows = R + 2 * halo; g.o_group_rows = R;
+  g.a_mode = 1;
+  g.bias = bias; g.act_split = D; g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
+  g.resid = h; g.ld_resid = D; g.out = h; g.ld_out = D; g.out_f32 = 1;
+  g.mask_len = nullptr; g.mask_period = 1;
+  return g;
+}
+
 int check_ready(const w2vseg_handle* h) {
   if (h == nullptr) { set_error("null handle"); return W2VSEG_ERR_ARG; }
   if (!h->finalized) {
@@ -326,16 +341,9 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
   {
     const int gc = D / c.pos_groups;
     W2V_REQUIRE(gc == 64, "positional conv: %d channels per group unsupported (64 only)", gc);
-    GemmProblem g = {};
-    g.A = w.zpad; g.a_rows = (int64_t)B * (R + 2 * kHalo) + 2 * kHalo; g.a_row_stride = D; g.a_cols = D;
-    g.W = h->pos_w; g.N = D; g.K = gc * c.pos_kernel;
-    g.num_groups = B; g.rows_per_group = R; g.a_group_rows = R + 2 * kHalo; g.o_group_rows = R;
-    g.a_mode = 1;
-    g.bias = h->pos_b; g.act_split = D; g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
-    g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
-    g.mask_len = nullptr; g.mask_period = 1;
+    GemmProblem g = posconv_problem(w.zpad, h->pos_w, h->pos_b, B, R, D, c.pos_kernel, w.h);
     prof_tag("gemm.pos_conv");
-    W2V_TRY(gemm_tc_launch(g, 64, st));
+    W2V_TRY(posconv_tc_launch(g, st));
   }
 
   // transformer layers (pre-LN "stable layer norm" variant, HF:632-655; adapter lib/models.py:404-428)
@@ -646,6 +654,15 @@ int32_t w2vseg_conv_gemm(const void* x, int64_t rows_out, int32_t C, int32_t kw,
   g.a_row_stride = (int64_t)stride * C;
   g.out = out; g.ld_out = N;
   return gemm_tc_launch(g, N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64), (cudaStream_t)stream);
+}
+
+int32_t w2vseg_posconv(const void* zpad, const void* W, const float* bias, int32_t B, int32_t R, int32_t D,
+                       int32_t taps, float* h, int32_t impl, void* stream) {
+  W2V_REQUIRE(zpad && W && h && B > 0 && R > 0, "posconv: bad argument");
+  W2V_REQUIRE(D % 64 == 0 && taps > 0 && taps % 2 == 0 && taps <= 128, "posconv: D=%d taps=%d unsupported", D, taps);
+  W2V_TRY(w2vseg_device_ok());
+  GemmProblem g = posconv_problem((const bf16*)zpad, (const bf16*)W, bias, B, R, D, taps, h);
+  return impl == 0 ? posconv_tc_launch(g, (cudaStream_t)stream) : gemm_tc_launch(g, 64, (cudaStream_t)stream);
 }
 
 int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C, const float* gamma,

@@ -55,4 +55,8 @@ int gemm_tc_launch(const GemmProblem& p, int block_n, cudaStream_t stream);
 // CTA-pair (cta_group::2) 256x256-tile variant: a_mode 0, N % 256 == 0 (gemm_tc2.cu).
 int gemm_tc2_launch(const GemmProblem& p, cudaStream_t stream);
 
+// Positional conv: same problem description as gemm_tc_launch(p, 64, ..) with a_mode 1, but the
+// 256-row input block of a tile stays resident in shared memory for all taps (posconv_tc.cu).
+int posconv_tc_launch(const GemmProblem& p, cudaStream_t stream);
+
 }  // namespace w2v
