@@ -178,7 +178,11 @@ def test_layernorm(lib, C, in_f32, act):
 @pytest.mark.parametrize("impl", ["w2vseg_attention", "w2vseg_attention_mma"])
 @pytest.mark.parametrize("heads,dh", [(16, 64), (8, 128)])
 @pytest.mark.parametrize("R,lens", [(1000, [999, 999]), (333, [333, 1, 200]), (130, [64, 65, 0, 130]),
-                                    (1100, [1099, 128, 129, 257])])
+                                    (1100, [1099, 128, 129, 257]),
+                                    # many items per persistent CTA, one-tile / empty items between long ones
+                                    # (ragged talk tails: a one-tile item between two others once deadlocked)
+                                    (1000, [999, 100, 999, 64, 128, 999, 1, 999, 129, 999, 50, 0, 999, 120]),
+                                    (640, [100] * 9 + [640, 100, 100, 300, 100] * 3)])
 def test_attention(lib, heads, dh, R, lens, impl):
     from wav2vecsegmenter_b200 import _native as n
 

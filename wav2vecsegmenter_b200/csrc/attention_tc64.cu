@@ -253,11 +253,17 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     cursor_skip_empty(Lc, n_items, stride, n_qt, heads, R, kv_len);
     Cursor Sc = Lc;   // next tile whose QK^T is to be issued
     Cursor Pc = Lc;   // next tile whose PV is to be issued
-    // K(g) [+ Q of its item when g is the item's first tile]; V(g) is loaded separately
+    // K(g) and V(g) are loaded separately; Q of an item goes with its first tile
+    auto load_q = [&](const Cursor& c) {
+      // The Q buffer doubles as the output staging tile of the item that used it two items ago: wait
+      // until that item's output store has read it. The softmax warps signal this at the start of
+      // the NEXT item, i.e. after an item epilogue that needs PV of that item's last tile — so this
+      // wait must only be reached after that PV has been issued (see the main loop), or a one-tile
+      // item in between deadlocks the CTA.
+      if (c.seq >= 2) mbar_wait(stage_free, (uint32_t)((c.seq - 2) & 1));
+      load_tile(sQ + (c.seq & 1) * A6_TILE_BYTES, &q_full[c.seq & 1], c.it.head * A6_DH, c.it.row_base + c.it.q0);
+    };
     auto load_k = [&](const Cursor& c, int g) {
-      // the Q buffer doubles as the output staging tile of the item that used it two items ago
-      if (c.j == 0 && c.seq >= 2) mbar_wait(stage_free, (uint32_t)((c.seq - 2) & 1));
-      if (c.j == 0) load_tile(sQ + (c.seq & 1) * A6_TILE_BYTES, &q_full[c.seq & 1], c.it.head * A6_DH, c.it.row_base + c.it.q0);
       load_tile(sK + (g & 1) * A6_TILE_BYTES, &k_full[g & 1], D + c.it.head * A6_DH, c.it.row_base + c.j * A6_BN);
     };
     auto load_v = [&](const Cursor& c, int g) {
@@ -287,10 +293,12 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 
     if (Lc.idx < n_items) {
       // prologue: tiles 0 and 1 in flight, S(0) issued
+      load_q(Lc);
       load_k(Lc, 0);
       load_v(Lc, 0);
       cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
       if (Lc.idx < n_items) {
+        if (Lc.j == 0) load_q(Lc);
         load_k(Lc, 1);
         load_v(Lc, 1);
         cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
@@ -303,8 +311,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         if (Sc.idx < n_items) {
           issue_s(Sc, g + 1);
           cursor_next(Sc, n_items, stride, n_qt, heads, R, kv_len);
-          // S(g) has retired (S(g+1) was issued after s_free(g)), so K buffer g&1 can be refilled;
-          // a Q buffer is refilled two items later, when every QK^T of its old item has retired too
+          // S(g) has retired (S(g+1) was issued after s_free(g)), so K buffer g&1 can be refilled
           if (Lc.idx < n_items) load_k(Lc, g + 2);
         }
         mbar_wait(&v_full[g & 1], (uint32_t)((g >> 1) & 1));
@@ -326,6 +333,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         }
         cursor_next(Pc, n_items, stride, n_qt, heads, R, kv_len);
         if (Lc.idx < n_items) {
+          if (Lc.j == 0) load_q(Lc);                 // (after PV(g) was issued: see load_q)
           mbar_wait(pv_done, (uint32_t)(g & 1));     // V buffer g&1 is free once PV(g) retired
           load_v(Lc, g + 2);
           cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
