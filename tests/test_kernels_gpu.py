@@ -103,6 +103,33 @@ def test_gemm_inplace_residual(lib):
     assert (h - ref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_attention_random_ragged_batches(lib, seed):
+    """persistent d=64 kernel: every CTA walks ~3-6 work items; random key lengths (empty, one-tile,
+    partial and full windows in any order) against the independent mma.sync implementation"""
+    from wav2vecsegmenter_b200 import _native as n
+
+    rng = torch.Generator().manual_seed(seed)
+    B, heads, dh = 14, 16, 64
+    R = int(torch.randint(300, 900, (1,), generator=rng))
+    lens = torch.randint(0, R + 1, (B,), generator=rng)
+    lens[torch.rand(B, generator=rng) < 0.3] = int(torch.randint(1, 129, (1,), generator=rng))   # one-tile windows
+    lens[torch.rand(B, generator=rng) < 0.1] = 0
+    D = heads * dh
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    qkv = torch.randn(B * R, 3 * D, device="cuda", generator=g).bfloat16()
+    kv_len = lens.to(device="cuda", dtype=torch.int32)
+    outs = []
+    for impl in ("w2vseg_attention", "w2vseg_attention_mma"):
+        ctx = torch.full((B * R, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+        n.check(getattr(lib, impl)(n.ptr(qkv), B, R, heads, dh, n.ptr(kv_len), dh ** -0.5, n.ptr(ctx),
+                                   n.current_stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(ctx.float())
+    assert torch.isfinite(outs[0]).all()
+    assert (outs[0] - outs[1]).abs().max().item() < 3e-2
+
+
 @pytest.mark.parametrize("kw,rows_out", [(3, 1999), (2, 999), (3, 31999)])
 def test_conv_as_implicit_gemm(lib, kw, rows_out):
     """stride-2 Conv1d over channels-last activations == GEMM over an overlapping-row TMA view"""
@@ -124,7 +151,7 @@ def test_conv_as_implicit_gemm(lib, kw, rows_out):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("B,R,D,taps", [(2, 300, 1024, 128), (3, 129, 128, 16), (1, 1000, 256, 128)])
+@pytest.mark.parametrize("B,R,D,taps", [(2, 300, 1024, 128), (3, 129, 128, 16), (1, 1000, 256, 128), (4, 50, 128, 128)])
 def test_posconv(lib, B, R, D, taps, impl):
     """grouped positional conv + GELU + residual (HF:326-379, 764-765): the resident-A kernel of the
     forward pass (impl 0) and the generic shifted-row GEMM (impl 1) against torch conv1d"""
