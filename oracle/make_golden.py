@@ -208,6 +208,69 @@ def gold_plan(ns, name):
     print(f"{name}: {len(recs)} plans")
 
 
+# ---- dev-set scoring path (lib/evaluate.py:130-214 + FixedSegmentationDataset, lib/dataset.py:335-498)
+EVAL_TALKS = [  # (id, n_samples, audio seed, true segments [start, end) in samples)
+    ("talk_a", 1_073_234, 60, [(8_000, 150_000), (150_000, 310_000), (333_333, 640_001), (655_000, 700_000),
+                               (905_000, 1_073_234)]),
+    ("talk_b", 500_017, 61, [(0, 90_000), (120_000, 320_000), (320_500, 480_000)]),
+]
+
+
+EVAL_POS_WEIGHT = 0.4
+
+
+def write_eval_corpus(root: Path):
+    """wav files + the two tsv lists the reference's data preparation produces (only the columns the
+    scoring path reads: talks id / path / total_frames, segments talk_id / start / end)"""
+    talks, segs = ["\tid\tpath\ttotal_frames"], ["\ttalk_id\tstart\tend"]
+    k = 0
+    for i, (tid, n, seed, true) in enumerate(EVAL_TALKS):
+        write_wav(root / f"{tid}.wav", synth.synthetic_audio(n, seed))
+        talks.append(f"{i}\t{tid}\t{root / (tid + '.wav')}\t{n}")
+        for a, b in true:
+            segs.append(f"{k}\t{tid}\t{a}\t{b}")
+            k += 1
+    (root / "talks.tsv").write_text("\n".join(talks) + "\n")
+    (root / "segments.tsv").write_text("\n".join(segs) + "\n")
+    return root / "talks.tsv", root / "segments.tsv"
+
+
+def gold_eval(ns, name, spec, seed, inference_times, batch_size):
+    """FixedDataloaderGenerator -> infer (with targets) -> evaluate, all from the unmodified reference"""
+    m, _ = build_reference_model(ns, spec, seed)
+    loss_fn = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(EVAL_POS_WEIGHT), reduction="none")
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        talk_list, seg_list = write_eval_corpus(Path(td))
+        gen = ns.dataset.FixedDataloaderGenerator(str(talk_list), str(seg_list), 20, batch_size, 0, inference_times)
+        for tid, *_ in EVAL_TALKS:
+            for i in range(inference_times):
+                dl = gen.generate(tid, i)
+                df = gen.dataset.fixed_segments_df
+                out[f"{tid}_{i}_starts"] = df.start.to_numpy().astype(np.int64)
+                out[f"{tid}_{i}_ends"] = df.end.to_numpy().astype(np.int64)
+                out[f"{tid}_{i}_included"] = np.array(json.dumps(list(df.included)))
+                items = [gen.dataset[k] for k in range(len(gen.dataset))]
+                out[f"{tid}_{i}_targets"] = np.concatenate([t[1].numpy() for t in items])
+                out[f"{tid}_{i}_target_lens"] = np.array([len(t[1]) for t in items])
+                out[f"{tid}_{i}_frames"] = np.array([[t[2], t[3]] for t in items], dtype=np.int64)
+                p, l, t, loss = ns.evaluate.infer(m, dl, torch.device("cpu"), False, "bce", None, loss_fn)
+                out[f"{tid}_{i}_probs"] = p
+                out[f"{tid}_{i}_talk_targets"] = t
+                out[f"{tid}_{i}_loss"] = float(loss)
+            out[f"{tid}_duration_outframes"] = int(gen.dataset.duration_outframes)
+        # loss_fn as train.py builds it from conf/task/shas.yaml (:25-30, train.py:355-374); without one
+        # the reference's evaluate() dies on an unbound `eval_loss` (lib/evaluate.py:211)
+        res = ns.evaluate.evaluate(gen, m, torch.device("cpu"), False, "bce", None, loss_fn)
+    out["metrics"] = np.array(json.dumps({k: float(v) for k, v in res.items()}))
+    out["pos_weight"] = EVAL_POS_WEIGHT
+    np.savez_compressed(
+        GOLD / f"{name}.npz",
+        spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads]),
+        seed=seed, inference_times=inference_times, batch_size=batch_size, **out)
+    print(f"{name}: metrics {res}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -232,6 +295,9 @@ def main():
         # whole-talk path with overlapped tilings (configs[3] shape): 67 s + odd samples
         "tiny_talk": lambda: gold_talk(ns, "tiny_talk", synth.TINY, 0, 1_073_234, 50, 2, 3),
         "tiny_talk_x1": lambda: gold_talk(ns, "tiny_talk_x1", synth.TINY, 0, 753_234, 51, 1, 14),
+        # dev-set scoring: two talks with labelled segments, two tilings
+        "tiny_eval": lambda: gold_eval(ns, "tiny_eval", synth.TINY, 0, 2, 3),
+        "tiny_eval_x1": lambda: gold_eval(ns, "tiny_eval_x1", synth.TINY, 0, 1, 14),
     }
     for k, fn in jobs.items():
         if args.only is None or args.only == k:

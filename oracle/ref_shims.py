@@ -10,6 +10,8 @@ under tests/golden/ (see oracle/make_golden.py). Five shims, exactly those SURVE
   4. torchaudio.info / torchaudio.backend.sox_io_backend.load re-created on top of `wave` and
      scipy (lib/dataset.py:596-598, 659-663; both APIs are gone in torchaudio 2.11)
   5. np.int = int                                   (lib/segment.py:431; removed in numpy 2)
+  6. int(pandas.Series of length 1)                 (lib/dataset.py:372,414 on the dev-set scoring
+     path; removed in pandas 3 — restored as Series.__int__ = int(self.iloc[0]))
 """
 from __future__ import annotations
 
@@ -67,6 +69,12 @@ def install():
             del sys.modules[k]
         if not hasattr(np, "int"):
             np.int = int  # noqa: NPY001
+        import pandas as pd
+
+        try:
+            int(pd.Series([3]))
+        except TypeError:
+            pd.Series.__int__ = lambda self: int(self.iloc[0])
         h = types.ModuleType("hydra")
         hu = types.ModuleType("hydra.utils")
         hu.instantiate = lambda *a, **k: None

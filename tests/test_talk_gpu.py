@@ -141,6 +141,46 @@ def test_dropin_modules_match_reference(tmp_path, tiny_engine):
     assert np.abs(acc - g["probs_avg"]).max() <= PROB_TOL
 
 
+@pytest.mark.parametrize("name", ["tiny_eval", "tiny_eval_x1"])
+def test_dev_set_scoring_matches_reference(tmp_path, name):
+    """FixedDataloaderGenerator -> infer (targets, loss) -> evaluate on the drop-in
+    modules with the CUDA model, against the reference's own run of the same corpus"""
+    import json
+
+    from oracle.make_golden import EVAL_TALKS, write_eval_corpus
+
+    for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.") or k in ("constants", "datautils")]:
+        del sys.modules[k]
+    from lib.dataset import FixedDataloaderGenerator
+    from lib.evaluate import evaluate, infer
+    from lib.models import SHAS
+
+    g = load_gold(name)
+    spec = spec_of(g)
+    dev = torch.device("cuda:0")
+    model = SHAS("facebook/wav2vec2-xls-r-300m", spec.keep_layers, True, spec.adapter_layers, False, False,
+                 True, spec.head_layers, spec.head_heads, 0.1).to(dev)
+    model.load_state_dict(synth.random_state_dict(spec, int(g["seed"])))
+    model.eval()
+    it, bs = int(g["inference_times"]), int(g["batch_size"])
+    tl, sl = write_eval_corpus(tmp_path)
+    gen = FixedDataloaderGenerator(str(tl), str(sl), 20, bs, 0, it)
+    loss_fn = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(float(g["pos_weight"]), device=dev), reduction="none")
+    for tid, *_ in EVAL_TALKS:
+        for i in range(it):
+            p, _, t, loss = infer(model, gen.generate(tid, i), dev, False, "bce", None, loss_fn)
+            assert np.array_equal(t, g[f"{tid}_{i}_talk_targets"])                  # labels: exact
+            assert np.abs(p - g[f"{tid}_{i}_probs"]).max() <= PROB_TOL
+            assert abs(loss - float(g[f"{tid}_{i}_loss"])) <= 0.02 * float(g[f"{tid}_{i}_loss"])
+    res = evaluate(gen, model, dev, False, "bce", None, loss_fn)
+    ref = json.loads(str(g["metrics"]))
+    assert set(res) == set(ref)
+    for k in ("eval_accuracy", "eval_f1", "eval_precision", "eval_recall"):
+        assert abs(float(res[k]) - ref[k]) <= 0.03, (k, res[k], ref[k])             # threshold flips within 2e-2
+    assert abs(float(res["eval_loss"]) - ref["eval_loss"]) <= 0.02 * ref["eval_loss"]
+    print(f"PARITY {name}: metrics {res} vs reference {ref}")
+
+
 def test_talk_reduction_kernels_bit_exact(tiny_engine):
     """scatter / NaN fill / tiling average / moving average == the host oracle, bit for bit"""
     from oracle import host_oracle as ho
