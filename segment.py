@@ -88,10 +88,15 @@ def generate(config, wav_paths=None) -> list:
     if wav_paths is None:
         wav_paths = [Path(config.infer_data.wav_dir) / n for n in wav_names(config)]
     yaml_content = []
-    for wav_path in wav_paths:
-        wave, sr = read_wav(wav_path)
-        assert sr == 16000, "Audio needs to have sample rate of 16000"
-        result = runner.run([wave])[0]
+
+    def waves():
+        for wav_path in wav_paths:
+            wave, sr = read_wav(wav_path)
+            assert sr == 16000, "Audio needs to have sample rate of 16000"
+            yield wave
+
+    # pipelined over talks: decode + H2D of the next wav overlap the forward of the current one
+    for wav_path, result in zip(wav_paths, runner.run_stream(waves())):
         segments = run_algorithm(config, result.probs)
         yaml_content = update_yaml_content(yaml_content, segments, Path(wav_path).name)
     del model

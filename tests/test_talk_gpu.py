@@ -181,6 +181,21 @@ def test_dev_set_scoring_matches_reference(tmp_path, name):
     print(f"PARITY {name}: metrics {res} vs reference {ref}")
 
 
+def test_run_stream_equals_run(tiny_engine):
+    """the pipelined throughput API returns, talk by talk, exactly what run() returns"""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    runner = TalkRunner(tiny_engine, batch_size=3, inference_times=2)
+    waves = [pcm_wave(n, 300 + i)[1] for i, n in enumerate([400_123, 47_000, 1_073_234, 320_000, 90_001])]
+    ref = [runner.run([w])[0] for w in waves]
+    for depth in (1, 2, 3):
+        got = list(runner.run_stream(iter(waves), depth=depth))
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a.probs, b.probs)
+            assert all(np.array_equal(x, y) for x, y in zip(a.per_tiling, b.per_tiling))
+
+
 def test_talk_reduction_kernels_bit_exact(tiny_engine):
     """scatter / NaN fill / tiling average / moving average == the host oracle, bit for bit"""
     from oracle import host_oracle as ho

@@ -241,9 +241,9 @@ class TalkRunner:
             rows = gather_rows(rows, len(wins), world, self.dist_group)
         return self.reduce(rows, wins, n_frames)
 
-    def reduce(self, rows, wins: list[Window], n_frames: list[int]) -> list[TalkResult]:
-        """rows [len(wins), r] (device) -> per-talk averaged probabilities (scatter, NaN fill,
-        tiling average on the device; one D2H per talk)"""
+    def reduce_device(self, rows, wins: list[Window], n_frames: list[int]):
+        """rows [len(wins), r] (device) -> per talk (avg float64 [n], tilings float64 [inference_times, n]) on
+        the device: scatter, NaN fill and tiling average kernels, no host round trip"""
         import torch
 
         eng = self.engine
@@ -258,9 +258,82 @@ class TalkRunner:
                 talk = eng.scatter_rows(talk_rows, st, ct, n, flag_col=talk_rows.shape[1] - 1)
                 eng.nanfill(talk, nan_idx)
                 tilings[i] = talk
-            avg = eng.overlap_average(tilings)
-            out.append(TalkResult(avg.cpu().numpy(), [tilings[i].cpu().numpy() for i in range(self.inference_times)]))
+            out.append((eng.overlap_average(tilings), tilings))
         return out
+
+    def reduce(self, rows, wins: list[Window], n_frames: list[int]) -> list[TalkResult]:
+        """rows [len(wins), r] (device) -> per-talk averaged probabilities on the host"""
+        return [TalkResult(avg.cpu().numpy(), [til[i].cpu().numpy() for i in range(self.inference_times)])
+                for avg, til in self.reduce_device(rows, wins, n_frames)]
+
+    def run_stream(self, talks, depth: int = 2):
+        """Throughput API: yields one TalkResult per input talk (same values as run([wave])[0]), with a
+        `depth`-deep software pipeline across talks — the host->device copy of talk k+1 and the
+        device->host copy of talk k-1 run on a side stream while the forward of talk k computes.
+        `talks` is an iterable of float32 sample arrays (pinned host memory makes the copies truly
+        asynchronous). Replaces the reference's per-talk loop with its blocking copies
+        (segment.py:71-124, lib/evaluate.py:36-44,96-97)."""
+        import torch
+
+        eng = self.engine
+        main = torch.cuda.current_stream(eng.device)
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(eng.device)
+        inflight = []      # (done_event, avg_host, tilings_host)
+        slots = [None] * depth   # device wave buffers + the event after which they may be overwritten
+
+        def finish(item):
+            ev, avg_h, til_h = item
+            ev.synchronize()
+            return TalkResult(avg_h.numpy().copy(), [til_h[i].numpy().copy() for i in range(self.inference_times)])
+
+        for k, wave in enumerate(talks):
+            wave = np.ascontiguousarray(wave, dtype=np.float32)
+            host = torch.from_numpy(wave)
+            slot = k % depth
+            with torch.cuda.stream(side):
+                if slots[slot] is not None:
+                    side.wait_event(slots[slot][1])          # forward of talk k-depth has consumed the buffer
+                if slots[slot] is None or slots[slot][0].numel() < host.numel():
+                    buf = torch.empty(host.numel(), dtype=torch.float32, device=eng.device)
+                else:
+                    buf = slots[slot][0]
+                dev = buf[: host.numel()]
+                dev.copy_(host, non_blocking=True)
+                h2d = torch.cuda.Event()
+                h2d.record(side)
+            main.wait_event(h2d)
+            wins, n_frames = self.plan([wave])
+            r_max = max([eng.frame_stride(max(w.n_samples, 400)) for w in wins] + [1])
+            world, rank = 1, 0
+            if self.dist_group is not None:
+                import torch.distributed as dist
+
+                world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
+            lo, hi = shard_ranges(len(wins), world)[rank]
+            rows = self._forward_rows({0: dev}, wins[lo:hi], r_max)
+            if world > 1:
+                rows = gather_rows(rows, len(wins), world, self.dist_group)
+            avg, til = self.reduce_device(rows, wins, n_frames)[0]
+            fwd = torch.cuda.Event()
+            fwd.record(main)
+            slots[slot] = (buf, fwd)
+            with torch.cuda.stream(side):
+                side.wait_event(fwd)
+                avg_h = torch.empty(avg.shape, dtype=avg.dtype, pin_memory=True)
+                til_h = torch.empty(til.shape, dtype=til.dtype, pin_memory=True)
+                avg_h.copy_(avg, non_blocking=True)
+                til_h.copy_(til, non_blocking=True)
+                avg.record_stream(side)
+                til.record_stream(side)
+                d2h = torch.cuda.Event()
+                d2h.record(side)
+            inflight.append((d2h, avg_h, til_h))
+            if len(inflight) >= depth:
+                yield finish(inflight.pop(0))
+        while inflight:
+            yield finish(inflight.pop(0))
 
 
 def gather_rows(rows, n_total: int, world: int, group=None):
