@@ -42,3 +42,20 @@ audio = dev.view(14, 320000)
 lens = torch.full((14,), 320000, dtype=torch.int32, device="cuda")
 ol = torch.full((14,), 999, dtype=torch.int32, device="cuda")
 print(f"sfc_forward (resident) {timed(lambda: eng.sfc_forward(audio, lens, lens, ol, 320000)):.3f} ms")
+
+# host-side (enqueue) cost of one step: no synchronisation inside the loop
+def host_only(fn, n=3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    return (t1 - t0) / n * 1e3
+
+
+print(f"host enqueue: _forward_rows {host_only(lambda: runner._forward_rows({0: dev}, wins, r_max)):.3f} ms, "
+      f"reduce_device {host_only(lambda: runner.reduce_device(rows, wins, n_frames)):.3f} ms, "
+      f"sfc_forward {host_only(lambda: eng.sfc_forward(audio, lens, lens, ol, 320000)):.3f} ms")
+t = timed(lambda: [None for _ in runner.run_stream((talk for _ in range(10)), depth=2)], n=3) / 10
+print(f"run_stream per talk    {t:.3f} ms")
