@@ -139,3 +139,32 @@ def test_window_independent_of_batch_composition():
     a = p_pair[1, : ol[1]].cpu()
     b = p_single[0, : ol[1]].cpu()
     assert (a - b).abs().max().item() < 1e-5
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] at full size (large 24/24 + adapters, 14 x 20 s): size-independent
+    properties instead of a CPU comparison — the first two windows equal the reference golden of the
+    same model (`large_batch`), every window equals its own single-window run (what lets windows be
+    batched and sharded freely), the run is deterministic, probabilities are finite and in (0, 1)."""
+    g = load_gold("large_batch")
+    spec = spec_of(g)
+    eng = engine_for(spec, int(g["seed"]))
+    B, L = 14, 320000
+    lens = [L] * B
+    raw = torch.zeros(B, L)
+    raw[:2] = make_batch([int(x) for x in g["lens"]], int(g["audio_seed"]))
+    raw[2:] = make_batch([L] * (B - 2), 4242)
+    raw[9, 200_000:] = 0            # a window that is silent in its second half
+    ol = out_lens_ref(lens)
+    dev = raw.cuda()
+    _, p = eng.sfc_forward(dev, lens, lens, ol, L)
+    p = p.clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(p).all() and (p[:, : ol[0]] > 0).all() and (p[:, : ol[0]] < 1).all()
+    ref = torch.from_numpy(g["probs"])
+    assert (p[:2, : ref.shape[1]].cpu() - ref).abs().max().item() <= PROB_TOL
+    _, p2 = eng.sfc_forward(dev, lens, lens, ol, L)
+    assert torch.equal(p, p2)                                   # deterministic, bit for bit
+    for i in (0, 9, 13):
+        _, pi = eng.sfc_forward(dev[i: i + 1].contiguous(), [L], [L], ol[i: i + 1], L)
+        assert (pi[0, : ol[i]] - p[i, : ol[i]]).abs().max().item() < 1e-5, i
