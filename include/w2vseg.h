@@ -199,6 +199,17 @@ int32_t w2vseg_conv_gemm(const void* x_bf16, int64_t rows_out, int32_t C, int32_
  * impl 1: the generic shifted-row GEMM (gemm_tc.cu, a_mode 1) kept as a second implementation. */
 int32_t w2vseg_posconv(const void* zpad_bf16, const void* W_bf16, const float* bias, int32_t B,
                        int32_t R, int32_t D, int32_t taps, float* h, int32_t impl, void* stream);
+/* Conv layer 0 (Conv1d(1, 512, k=10, stride=5, bias) -> LayerNorm(512) -> GELU, HF:281-299) with the
+ * window normalisation (x - mean) * rstd applied on the fly (lib/datautils.py:122-125).
+ * audio fp32 [B, audio_stride]; samples at or beyond sample_len[b] read as 0; stats fp32 [B][2] =
+ * (mean, 1/std) per window; w fp32 [512, 10]; out bf16 [B*R0, 512] channels-last (frame t of window b
+ * in row b*R0 + t). impl 0: the forward pass's tcgen05 kernel (LayerNorm folded into a K=16 fp16 MMA,
+ * conv0_tc.cu); impl 1: the CUDA-core kernel kept as a second implementation. scratch: >= 64 KiB of
+ * device memory for the packed weights. */
+int32_t w2vseg_conv0(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                     const float* stats, const float* w, const float* bias, const float* gamma,
+                     const float* beta, float eps, void* out_bf16, int32_t B, int32_t R0,
+                     int32_t impl, void* scratch, size_t scratch_bytes, void* stream);
 /* LayerNorm over the last dim (C = 512 or 1024). in: fp32 or bf16; out: bf16; act 0/1 (GELU). */
 int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C,
                          const float* gamma, const float* beta, float eps, int32_t act,

@@ -178,6 +178,54 @@ def test_posconv(lib, B, R, D, taps, impl):
     assert err < 5e-3, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize(
+    "R0,lens,case",
+    [
+        (640, [3205, 3205], "plain"),                 # 5 frame blocks per window, all samples valid
+        (320, [1605, 700, 0, 1605], "ragged"),        # 2.5 blocks per window (row predicate), short + empty windows
+        (64000, [320000], "full"),                    # one 20 s window: persistent loop, TMEM double buffering
+        (1280, [6405, 6000, 6405], "const_bias"),     # constant bias + a dead tap: semi-definite Gram matrix
+    ],
+)
+def test_conv0(lib, R0, lens, case, impl):
+    """conv layer 0 + LayerNorm(512) + GELU with on-the-fly window normalisation (HF:281-299): the
+    tcgen05 kernel with the LayerNorm folded into the MMA (impl 0) and the CUDA-core kernel (impl 1)
+    against torch conv1d -> layer_norm -> gelu in fp32."""
+    from wav2vecsegmenter_b200 import _native as n
+
+    B = len(lens)
+    g = torch.Generator(device="cuda").manual_seed(R0 + B)
+    stride = R0 * 5 + 8
+    audio = torch.randn(B, stride, device="cuda", generator=g) * 0.3 + 0.05
+    w = torch.randn(512, 10, device="cuda", generator=g) / math.sqrt(10)
+    bias = torch.randn(512, device="cuda", generator=g) * 0.2
+    gamma = torch.randn(512, device="cuda", generator=g)
+    beta = torch.randn(512, device="cuda", generator=g) * 0.5
+    if case == "const_bias":
+        bias.fill_(0.25)
+        w[:, 3] = 0.0
+    slen = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    stats = torch.stack([torch.full((B,), 0.05, device="cuda"), torch.full((B,), 1 / 0.3, device="cuda")], dim=1).contiguous()
+    out = torch.full((B * R0, 512), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scratch = torch.empty(65536, device="cuda", dtype=torch.uint8)
+    n.check(lib.w2vseg_conv0(n.ptr(audio), stride, n.ptr(slen), n.ptr(stats), n.ptr(w), n.ptr(bias), n.ptr(gamma),
+                             n.ptr(beta), 1e-5, n.ptr(out), B, R0, impl, n.ptr(scratch), scratch.numel(),
+                             n.current_stream_ptr()), "conv0")
+    torch.cuda.synchronize()
+    idx = torch.arange(R0 * 5 + 5, device="cuda")
+    xn = torch.where(idx[None, :] < slen[:, None], (audio[:, : R0 * 5 + 5] - 0.05) * (1 / 0.3), torch.zeros((), device="cuda"))
+    y = torch.nn.functional.conv1d(xn[:, None, :].double(), w[:, None, :].double(), bias.double(), stride=5)   # [B, 512, R0]
+    assert y.shape[2] == R0
+    y = torch.nn.functional.layer_norm(y.transpose(1, 2), (512,), gamma.double(), beta.double(), 1e-5)
+    ref = torch.nn.functional.gelu(y).float().reshape(B * R0, 512)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs()
+    # bf16 output (2^-9 relative) + fp16 operands of the folded MMA (2^-11 per factor) + MUFU.TANH
+    assert (err <= 1e-2 + 8e-3 * ref.abs()).all(), f"max abs err {err.max().item()}"
+    assert err.mean().item() < 2e-3
+
+
 @pytest.mark.parametrize("C,in_f32,act", [(1024, True, 0), (512, False, 0), (512, False, 1), (512, True, 0)])
 def test_layernorm(lib, C, in_f32, act):
     from wav2vecsegmenter_b200 import _native as n

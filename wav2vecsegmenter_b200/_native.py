@@ -71,6 +71,7 @@ SIGNATURES = {
     "w2vseg_gemm": (_I32, [_P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _I32, _I32, _P]),
     "w2vseg_conv_gemm": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P]),
     "w2vseg_posconv": (_I32, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
+    "w2vseg_conv0": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P, C.c_float, _P, _I32, _I32, _I32, _P, _SZ, _P]),
     "w2vseg_layernorm": (_I32, [_P, _I32, _I64, _I32, _P, _P, C.c_float, _I32, _P, _P]),
     "w2vseg_attention": (_I32, [_P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),
     "w2vseg_attention_mma": (_I32, [_P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),

@@ -3,6 +3,9 @@
 // One handle = one SFC model replica on the current device (one process per GPU). The forward
 // pass is a fixed sequence of launches on the caller's stream; it allocates nothing and performs
 // no host synchronisation, so the host can capture it into a CUDA graph or run it ahead.
+#include <stdlib.h>
+#include <string.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -74,6 +77,8 @@ struct w2vseg_handle {
   size_t arena_bytes = 0, arena_used = 0;
   // weights
   float* conv0_wt = nullptr;
+  uint8_t* conv0_pack = nullptr;   // fp16 LayerNorm-folded weights + variance factor (conv0_tc.cu)
+  bool conv0_cuda_cores = false;   // W2VSEG_CONV0=cuda: the CUDA-core kernel (A/B measurements)
   float* conv_b[7] = {};
   LNW conv_ln[7];
   bf16* conv_w[7] = {};
@@ -124,6 +129,7 @@ void build_layout(w2vseg_handle* h) {
 
   // feature extractor
   h->conv0_wt = h->alloc<float>((size_t)10 * CD);
+  h->conv0_pack = h->alloc<uint8_t>(conv0_tc_pack_bytes());
   {
     Slot s; s.kind = SLOT_CONV0; s.numel = (int64_t)CD * 10; s.fdst = h->conv0_wt; s.O = CD; s.J = 10;
     h->slots["fe.conv0.weight"] = s;
@@ -309,8 +315,12 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
 
   // conv feature extractor (HF:382-419). Layer l activations: channels-last bf16 [B*R*2^(6-l), 512].
   const int R0 = R << 6;
-  W2V_TRY(conv0_ln_gelu_launch(audio, audio_stride, sample_len, w.stats, h->conv0_wt, h->conv_b[0],
-                               h->conv_ln[0].g, h->conv_ln[0].b, c.ln_eps, w.conv[0], B, R0, st));
+  if (h->conv0_cuda_cores)
+    W2V_TRY(conv0_ln_gelu_launch(audio, audio_stride, sample_len, w.stats, h->conv0_wt, h->conv_b[0],
+                                 h->conv_ln[0].g, h->conv_ln[0].b, c.ln_eps, w.conv[0], B, R0, st));
+  else
+    W2V_TRY(conv0_tc_launch(audio, audio_stride, sample_len, w.stats, h->conv0_pack, c.ln_eps,
+                            w.conv[0], B, R0, st));
   for (int l = 1; l < 7; ++l) {
     const int64_t rows_in = M << (7 - l), rows_out = M << (6 - l);
     // the last output row's im2col view runs (k-2) rows past the input: keep that slack finite
@@ -453,6 +463,10 @@ int32_t w2vseg_create(const w2vseg_config* cfg, w2vseg_handle** out) {
   h->D = cfg->hidden;
   h->DH = cfg->hidden / cfg->heads;
   h->F1max = cfg->ffn + (cfg->n_adapter_layers > 0 ? cfg->adapter_dim : 0);
+  {
+    const char* e = getenv("W2VSEG_CONV0");
+    h->conv0_cuda_cores = e != nullptr && strcmp(e, "cuda") == 0;
+  }
   if (cfg->head_layers > 0 && cfg->head_ffn > h->F1max) h->F1max = cfg->head_ffn;
   build_layout(h);  // sizing pass
   h->arena_bytes = h->arena_used + 4096;
@@ -526,6 +540,9 @@ int32_t w2vseg_finalize_weights(w2vseg_handle* h, void* stream) {
     W2V_TRY(weightnorm_scale_launch(h->pos_v, h->pos_g, h->D * gc, c.pos_kernel, h->pos_scale, st));
     W2V_TRY(pack_conv_launch(h->pos_v, h->D, gc, c.pos_kernel, h->pos_scale, h->pos_w, st));
   }
+  // conv layer 0: centred, gamma-scaled fp16 taps + Cholesky factor of the channel Gram matrix
+  W2V_TRY(conv0_tc_pack_launch(h->conv0_wt, 1, c.conv_dim, h->conv_b[0], h->conv_ln[0].g,
+                               h->conv_ln[0].b, h->conv0_pack, st));
   for (auto& L : h->enc) {
     if (L.adapter) W2V_TRY(axpby_launch(L.b2_raw, 1.f, L.bu_raw, c.adapter_scale, L.b2, h->D, st));
     else W2V_TRY(axpby_launch(L.b2_raw, 1.f, nullptr, 0.f, L.b2, h->D, st));
@@ -663,6 +680,25 @@ int32_t w2vseg_posconv(const void* zpad, const void* W, const float* bias, int32
   W2V_TRY(w2vseg_device_ok());
   GemmProblem g = posconv_problem((const bf16*)zpad, (const bf16*)W, bias, B, R, D, taps, h);
   return impl == 0 ? posconv_tc_launch(g, (cudaStream_t)stream) : gemm_tc_launch(g, 64, (cudaStream_t)stream);
+}
+
+int32_t w2vseg_conv0(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                     const float* stats, const float* w, const float* bias, const float* gamma,
+                     const float* beta, float eps, void* out, int32_t B, int32_t R0, int32_t impl,
+                     void* scratch, size_t scratch_bytes, void* stream) {
+  W2V_REQUIRE(audio && sample_len && stats && w && bias && gamma && beta && out && scratch,
+              "conv0: null argument");
+  W2V_REQUIRE(B > 0 && R0 > 0 && scratch_bytes >= 65536, "conv0: bad shape or scratch < 64 KiB");
+  W2V_TRY(w2vseg_device_ok());
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 0) {
+    W2V_TRY(conv0_tc_pack_launch(w, 10, 1, bias, gamma, beta, scratch, st));
+    return conv0_tc_launch(audio, audio_stride, sample_len, (const float2*)stats, scratch, eps, (bf16*)out, B, R0, st);
+  }
+  float* wt = reinterpret_cast<float*>(scratch);
+  W2V_TRY(transpose_f32_launch(w, 512, 10, wt, st));
+  return conv0_ln_gelu_launch(audio, audio_stride, sample_len, (const float2*)stats, wt, bias, gamma, beta, eps,
+                              (bf16*)out, B, R0, st);
 }
 
 int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C, const float* gamma,

@@ -18,6 +18,16 @@ int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t
                          const float* gamma, const float* beta, float eps, __nv_bfloat16* out,
                          int B, int R0, cudaStream_t s);
 
+// same layer on the tensor cores (conv0_tc.cu): LayerNorm folded into ONE K=16 fp16 tcgen05.mma per
+// 128-frame x 256-channel tile, GELU in the epilogue. `pack` = conv0_tc_pack_bytes() device bytes
+// filled once per weight set by conv0_tc_pack_launch (w element (c,k) at w[c*sc + k*sk]).
+size_t conv0_tc_pack_bytes();
+int conv0_tc_pack_launch(const float* w, int sc, int sk, const float* bias, const float* gamma,
+                         const float* beta, void* pack, cudaStream_t s);
+int conv0_tc_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                    const float2* stats, const void* pack, float eps, __nv_bfloat16* out, int B,
+                    int R0, cudaStream_t s);
+
 // LayerNorm over C (512 or 1024) per row, optional GELU; in fp32 or bf16, out bf16. in==out allowed
 // for bf16 input.
 int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const float* gamma,
