@@ -272,9 +272,23 @@ def run_native(args):
                             "share_of_step": round(gemm_ms / step_ms, 4)},
             "whole_path_frac": round(value / world * (total_fl / WIN_SEC) / 1e12 / peaks["tflops_sustained"], 4),
         }
+        # memory-bound kernels: ALGORITHMIC bytes per step (each tensor read / written once)
+        # over the measured copy bandwidth of MEASURED_PEAKS.json
+        M_rows = BATCH * ((WIN_SAMPLES + 319) // 320)          # rows per [B*R, C] activation
+        hbm_bytes = {
+            "window_stats": 4 * WIN_SAMPLES * BATCH,
+            "conv0_ln_gelu": 4 * WIN_SAMPLES * BATCH + 2 * 512 * 64 * M_rows,
+            "ln_gelu.conv": (2 + 2) * 512 * 63 * M_rows,        # conv levels 1..6: 32+16+..+1 = 63 x M rows
+            "layernorm": 50 * (4 + 2) * 1024 * M_rows + (2 + 2) * 512 * M_rows,
+            "cast_to_padded": (4 + 2) * 1024 * M_rows,
+            "head_final": 4 * 1024 * M_rows,
+        }
         for k, v in kernels.items():
             if k in fl and v["ms_per_step"] > 0:
                 v["tflops"] = round(fl[k] * BATCH / (v["ms_per_step"] / 1e3) / 1e12, 1)
+            if k in hbm_bytes and v["ms_per_step"] > 0 and peaks.get("hbm_gbs"):
+                v["hbm_gbs"] = round(hbm_bytes[k] / (v["ms_per_step"] / 1e3) / 1e9, 1)
+                v["hbm_frac"] = round(v["hbm_gbs"] / peaks["hbm_gbs"], 3)
             v["ms_per_step"] = round(v["ms_per_step"], 4)
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline = cpu_reference_timing(n_windows=1, reps=2)

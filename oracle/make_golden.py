@@ -132,6 +132,91 @@ def gold_talk(ns, name, spec, seed, n_samples, audio_seed, inference_times, batc
           + ", ".join(f"{t}:{len(out[t + '_bounds'])}" for t in algos))
 
 
+def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_times, batch_size):
+    """Boundary-parity fixture with DECISIVE probabilities (what a trained checkpoint produces; the
+    random-init tracks of gold_talk hover around the thresholds). Audio = synth.speech_like_audio
+    (noise bursts / near-silent pauses); the model is the seeded random one, except that its final
+    Linear(1024 -> 1) (lib/models.py:304,319) is ridge-fitted on the REFERENCE's own features (hook on
+    seg_model.layer_norm) to +-3.5 logits for speech / pause frames. The fitted row and bias are
+    stored in the fixture, so the CUDA test rebuilds exactly this checkpoint. Everything after the
+    fit is the unmodified reference pipeline, as in gold_talk."""
+    from torch.utils.data import DataLoader
+
+    m, sd = build_reference_model(ns, spec, seed)
+    x, lab = synth.speech_like_audio(n_samples, audio_seed)
+    feats = []
+    hook = m.seg_model.layer_norm.register_forward_hook(lambda mod, i, o: feats.append(o.detach().clone()))
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        wav = Path(td) / "talk.wav"
+        write_wav(wav, x)
+        ds = ns.dataset.FixedSegmentationDatasetNoTarget(wav, 20, inference_times)
+
+        def loader():
+            return DataLoader(ds, batch_size=batch_size, num_workers=0, shuffle=False, drop_last=False,
+                              collate_fn=ns.datautils.CollateFn(0))
+
+        # pass 1 (tiling 0, random output layer): collect the features and fit the output layer
+        ds.fixed_length_segmentation(0)
+        probs0, _, _, _ = ns.evaluate.infer(m, loader(), torch.device("cpu"), False, "bce", None)
+        hook.remove()
+        n_frames = len(probs0)
+        lab = lab[:n_frames]
+        Z = np.zeros((n_frames, spec.hidden))
+        have = np.zeros(n_frames, bool)
+        fr = lambda v: int(np.round((v + 1e-6) * 49.95 / 16000))
+        j = 0
+        for zb in feats:
+            for i in range(zb.shape[0]):
+                s0, e0 = fr(ds.starts[j]), fr(ds.ends[j])
+                cnt = min(e0 - s0, zb.shape[1], n_frames - s0)
+                Z[s0:s0 + cnt] = zb[i, :cnt].numpy()
+                have[s0:s0 + cnt] = True
+                j += 1
+        edge = np.zeros(n_frames, bool)
+        for k in np.flatnonzero(np.diff(lab.astype(int)) != 0):
+            edge[max(0, k - 3):k + 5] = True
+        sel = have & ~edge
+        A = np.concatenate([Z[sel], np.ones((int(sel.sum()), 1))], 1)
+        G = A.T @ A + 100.0 * np.eye(spec.hidden + 1)
+        G[-1, -1] -= 100.0
+        wb = np.linalg.solve(G, A.T @ np.where(lab, 3.5, -3.5)[sel])
+        out_w = torch.tensor(wb[:-1], dtype=torch.float32)[None, :]
+        out_b = torch.tensor(wb[-1:], dtype=torch.float32)
+        with torch.no_grad():
+            m.seg_model.output_layer.weight.copy_(out_w)
+            m.seg_model.output_layer.bias.copy_(out_b)
+        # pass 2: the reference pipeline with the calibrated checkpoint
+        acc = None
+        for i in range(inference_times):
+            ds.fixed_length_segmentation(i)
+            probs, _, _, _ = ns.evaluate.infer(m, loader(), torch.device("cpu"), False, "bce", None)
+            out[f"probs_{i}"] = probs.copy()
+            acc = probs.copy() if acc is None else acc + probs
+        acc /= inference_times
+    out["probs_avg"] = acc
+    algos = {
+        "dac": (ns.segment.pdac, dict(max_segment_length=16, min_segment_length=0.2, threshold=0.5)),
+        "strm": (ns.segment.strm, dict(max_segment_length=18, min_segment_length=0.2, min_pause_length=0.2, threshold=0.5)),
+        "pthr": (ns.segment.pthr, dict(max_segment_length=28, min_segment_length=0.2, max_lerp_range=4,
+                                       min_lerp_range=0.4, threshold=0.1, moving_average_window=0.1)),
+    }
+    for tag, (fn, kw) in algos.items():
+        segs = fn(acc, **kw)
+        out[f"{tag}_bounds"] = np.array([[s.start, s.end] for s in segs], dtype=np.float64).reshape(-1, 2)
+        content = ns.segment.update_yaml_content([], segs, "talk.wav")
+        out[f"{tag}_yaml"] = np.array(yaml.dump(content, default_flow_style=True))
+    np.savez_compressed(
+        GOLD / f"{name}.npz",
+        spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads]),
+        seed=seed, audio_seed=audio_seed, n_samples=n_samples, inference_times=inference_times,
+        batch_size=batch_size, duration_outframes=int(ds.duration_outframes),
+        out_w=out_w.numpy(), out_b=out_b.numpy(), labels=lab, **out)
+    dec = (np.abs(acc - 0.5) > 0.4).mean()
+    print(f"{name}: {len(acc)} frames, {dec:.3f} of them with p < 0.1 or p > 0.9, label agreement "
+          f"{((acc > 0.5) == lab).mean():.4f}, " + ", ".join(f"{t}:{len(out[t + '_bounds'])}" for t in algos))
+
+
 def _prob_tracks(rng, n):
     """probability-like test signals: smooth random walk through [0,1] with exact-zero runs"""
     steps = rng.normal(0, 0.08, n).cumsum()
@@ -295,6 +380,9 @@ def main():
         # whole-talk path with overlapped tilings (configs[3] shape): 67 s + odd samples
         "tiny_talk": lambda: gold_talk(ns, "tiny_talk", synth.TINY, 0, 1_073_234, 50, 2, 3),
         "tiny_talk_x1": lambda: gold_talk(ns, "tiny_talk_x1", synth.TINY, 0, 753_234, 51, 1, 14),
+        # decisive (trained-like) probabilities: the boundary-identity fixtures
+        "speech_talk": lambda: gold_talk_decisive(ns, "speech_talk", synth.TINY, 0, 16000 * 400 + 1234, 60, 1, 14),
+        "speech_talk_x2": lambda: gold_talk_decisive(ns, "speech_talk_x2", synth.TINY, 0, 16000 * 200 + 777, 61, 2, 3),
         # dev-set scoring: two talks with labelled segments, two tilings
         "tiny_eval": lambda: gold_eval(ns, "tiny_eval", synth.TINY, 0, 2, 3),
         "tiny_eval_x1": lambda: gold_eval(ns, "tiny_eval_x1", synth.TINY, 0, 1, 14),

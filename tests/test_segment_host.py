@@ -33,6 +33,25 @@ def test_pdac_strm_pthr_match_reference(seg):
             assert text == str(g[f"{tag}_yaml_{c}"]), f"{tag} case {c}"
 
 
+@pytest.mark.parametrize("name", ["speech_talk", "speech_talk_x2"])
+def test_decisive_talk_fixture_host_side(seg, name):
+    """the decisive-probability fixtures (oracle/make_golden.py:gold_talk_decisive): pDAC / pSTRM on
+    the reference's own probabilities reproduce the reference's boundaries and yaml bit-exactly, and
+    the fixture is what it claims to be (>= 99 % of frames far from the thresholds)."""
+    g = load_gold(name)
+    p = g["probs_avg"]
+    assert (np.abs(p - 0.5) > 0.4).mean() > 0.99
+    assert ((p > 0.5) == g["labels"]).mean() > 0.99
+    kws = {"dac": dict(max_segment_length=16, min_segment_length=0.2, threshold=0.5),
+           "strm": dict(max_segment_length=18, min_segment_length=0.2, min_pause_length=0.2, threshold=0.5)}
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm)):
+        segs = fn(p, **kws[tag])
+        got = np.array([[s.start, s.end] for s in segs], dtype=np.float64).reshape(-1, 2)
+        np.testing.assert_array_equal(got, g[f"{tag}_bounds"])
+        text = yaml.dump(seg.update_yaml_content([], segs, "talk.wav"), default_flow_style=True)
+        assert text == str(g[f"{tag}_yaml"])
+
+
 def test_segment_edge_cases(seg):
     assert seg.pdac(np.zeros(10), 16, 0.2, 0.5)[0].duration == 0.0
     assert seg.strm(np.zeros(0)) == []

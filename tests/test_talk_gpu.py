@@ -104,6 +104,62 @@ def test_talk_probs_and_segments(name, tiny_engine, seg):
               f"max-abs prob err {np.abs(res.probs - ref_p).max():.4f}, mean {np.abs(res.probs - ref_p).mean():.5f}")
 
 
+def speech_wave(n, seed):
+    x, _ = synth.speech_like_audio(n, seed)
+    pcm = torch.round(x * 32767.0).clamp(-32768, 32767).to(torch.int16)
+    return (pcm.float() / 32768.0).numpy()
+
+
+def test_boundaries_identical_on_decisive_probabilities(seg):
+    """north_star: pDAC / pSTRM boundaries from the CUDA path's probabilities identical to the
+    reference's on >= 99 % of boundaries. Demonstrated where the claim is meaningful: talk-like signals
+    (noise bursts / pauses; one tiling and two overlapped tilings) and a checkpoint whose output layer
+    was fitted (by oracle/make_golden.py, on the reference's own features) so that the probabilities
+    are decisive, as a trained model's are. The golden boundaries come from the unmodified reference
+    pipeline in fp32. pDAC picks its split among the lowest-probability frames of a segment
+    (lib/segment.py:213): two pauses whose minima differ by less than the arithmetic noise can swap,
+    which moves both boundaries of one split -- hence >= 99 % over the fixtures, not 100 %."""
+    from wav2vecsegmenter_b200.engine import SFCEngine
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    n_ref = n_same = n_near = 0
+    for name in ("speech_talk", "speech_talk_x2"):
+        g = load_gold(name)
+        sd = synth.random_state_dict(synth.TINY, int(g["seed"]))
+        sd["seg_model.output_layer.weight"] = torch.from_numpy(g["out_w"].copy())
+        sd["seg_model.output_layer.bias"] = torch.from_numpy(g["out_b"].copy())
+        eng = SFCEngine(synth.TINY)
+        eng.load_state_dict(sd)
+        it = int(g["inference_times"])
+        wave_f = speech_wave(int(g["n_samples"]), int(g["audio_seed"]))
+        res = TalkRunner(eng, batch_size=int(g["batch_size"]), segment_sec=20, inference_times=it).run([wave_f])[0]
+        ref_p = g["probs_avg"]
+        assert len(res.probs) == len(ref_p)
+        err = np.abs(res.probs - ref_p)
+        assert err.max() <= PROB_TOL, err.max()
+        t_ref = t_same = 0
+        for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+            segs = fn(res.probs, **ALGOS[tag])
+            got = np.array([[s.start, s.end] for s in segs]).reshape(-1, 2)
+            ref = g[f"{tag}_bounds"]
+            exact = boundary_agreement(got, ref, tol=0.0)
+            near = boundary_agreement(got, ref, tol=1.0)
+            print(f"PARITY {name} {tag}: {len(segs)} segments vs {len(ref)}; boundaries identical {exact:.4f}, within one frame {near:.4f}")
+            assert len(segs) == len(ref), tag
+            if tag != "pthr":          # north_star names pDAC and pSTRM
+                t_ref += ref.size
+                t_same += int(round(exact * ref.size))
+                n_near += int(round(near * ref.size))
+        print(f"PARITY {name}: pDAC+pSTRM {t_same}/{t_ref} boundaries identical ({t_same / t_ref:.4f}); "
+              f"max-abs prob err {err.max():.4f}, mean {err.mean():.5f}")
+        assert t_same / t_ref >= 0.95, name
+        n_ref += t_ref
+        n_same += t_same
+    print(f"PARITY decisive talks: pDAC+pSTRM {n_same}/{n_ref} boundaries identical ({n_same / n_ref:.4f}), "
+          f"{n_near / n_ref:.4f} within one frame")
+    assert n_same / n_ref >= 0.99
+
+
 def test_dropin_modules_match_reference(tmp_path, tiny_engine):
     """the reference's own call sequence (segment.py:71-108) on the drop-in lib.* modules"""
     from torch.utils.data import DataLoader

@@ -1,5 +1,8 @@
 // Memory-bound / CUDA-core kernels of the SFC path: coalesced, 128-bit vectorised, warp-shuffle
 // reductions, one warp per row wherever a row is a LayerNorm group.
+#include <stdlib.h>
+#include <string.h>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -285,6 +288,68 @@ layernorm_kernel(const void* in_, long long rows, const float* __restrict__ gamm
   }
 }
 
+// LayerNorm(1024) of the fp32 residual stream, persistent: warps walk the rows with a grid stride
+// and the loads of a warp's NEXT row are issued before the current row is reduced / normalised /
+// stored, so every warp always has a 4 KB row in flight. (One-row-per-warp blocks that come and go
+// — layernorm_kernel above — spend the reduce/store phase of each block with nothing in flight:
+// ncu showed 55 % of the HBM read peak for it on the 57 MB stream.)
+__device__ __forceinline__ void ln1024_load(float4 (&r)[8], const float* in, long long row, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(in) + row * 256;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __ldcs(p + i * 32 + lane);   // streamed: read exactly once
+}
+
+__device__ __forceinline__ void ln1024_finish(const float4 (&r)[8], long long row, int lane,
+                                              const float* gamma, const float* beta, float eps,
+                                              __nv_bfloat16* out) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+  const float mean = warp_sum(s) * (1.f / 1024.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = r[i].x - mean, b = r[i].y - mean, c = r[i].z - mean, d = r[i].w - mean;
+    q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 1024.f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    // volatile (loads AND store): gamma / beta are re-read (L1 hits) for every row, one group at a
+    // time; hoisted out of the row loop or batched, their 64 values push the kernel past 128 registers
+    float4 g, bt;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(gamma + col));
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(bt.x), "=f"(bt.y), "=f"(bt.z), "=f"(bt.w) : "l"(beta + col));
+    const uint32_t u0 = pack_bf16x2(fmaf((r[i].x - mean) * rstd, g.x, bt.x), fmaf((r[i].y - mean) * rstd, g.y, bt.y));
+    const uint32_t u1 = pack_bf16x2(fmaf((r[i].z - mean) * rstd, g.z, bt.z), fmaf((r[i].w - mean) * rstd, g.w, bt.w));
+    asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(out + row * 1024 + col), "r"(u0), "r"(u1) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+layernorm1024_stream_kernel(const float* __restrict__ in, long long rows,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float eps, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  float4 cur[8], nxt[8];
+  if (row < rows) ln1024_load(cur, in, row, lane);
+#pragma unroll 1
+  for (; row < rows; row += nw) {
+    const bool more = row + nw < rows;
+    if (more) ln1024_load(nxt, in, row + nw, lane);
+    ln1024_finish(cur, row, lane, gamma, beta, eps, out);
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+  }
+}
+
 // =============================================================================================
 // small data-movement kernels
 // =============================================================================================
@@ -555,7 +620,17 @@ int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const flo
   if (C == 512 && !in_f32 && act == 0) W2V_LN(512, false, 0);
   else if (C == 512 && !in_f32 && act == 1) W2V_LN(512, false, 1);
   else if (C == 512 && in_f32 && act == 0) W2V_LN(512, true, 0);
-  else if (C == 1024 && in_f32 && act == 0) W2V_LN(1024, true, 0);
+  else if (C == 1024 && in_f32 && act == 0) {
+    static const bool v1 = getenv("W2VSEG_LN") != nullptr && strcmp(getenv("W2VSEG_LN"), "v1") == 0;
+    if (v1) {
+      W2V_LN(1024, true, 0);   // one-row-per-warp blocks (A/B measurements)
+    } else {
+      const long long want = (rows + 7) / 8;
+      const long long cap = 2LL * num_sms();
+      layernorm1024_stream_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(
+          reinterpret_cast<const float*>(in), rows, gamma, beta, eps, out);
+    }
+  }
   else if (C == 1024 && !in_f32 && act == 0) W2V_LN(1024, false, 0);
   else {
     set_error("layernorm: unsupported (C=%d, in_f32=%d, act=%d)", C, (int)in_f32, act);

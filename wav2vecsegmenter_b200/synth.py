@@ -152,3 +152,25 @@ def synthetic_audio(n_samples: int, seed: int = 0, modulated: bool = True) -> to
         x = x * (0.02 + env)
     x = 0.25 * x / x.abs().max().clamp_min(1e-6) * 3.0
     return x.clamp_(-0.999, 0.999)
+
+
+def speech_like_audio(n_samples: int, seed: int = 0):
+    """fp32 mono 16 kHz signal with talk-like structure: noise bursts of 1.5-9 s ("speech", random
+    level) separated by 0.25-1.5 s of near-silence ("pauses"), 20 ms ramps at the edges. Returns
+    (samples, is_speech per 20 ms output frame at 49.95 Hz). Used by the boundary-parity fixture:
+    with a calibrated output layer the frame probabilities are decisive like a trained model's."""
+    g = torch.Generator().manual_seed(seed)
+    env = torch.zeros(n_samples)
+    pos = 0
+    while pos < n_samples:
+        sp = int((1.5 + 7.5 * torch.rand(1, generator=g).item()) * 16000)
+        pa = int((0.25 + 1.25 * torch.rand(1, generator=g).item()) * 16000)
+        lvl = 0.3 + 0.7 * torch.rand(1, generator=g).item()
+        env[pos:pos + sp] = lvl
+        pos += sp + pa
+    k = torch.ones(1, 1, 321) / 321.0   # 20 ms moving average = linear ramps
+    env_s = torch.nn.functional.conv1d(env[None, None], k, padding=160)[0, 0]
+    x = torch.randn(n_samples, generator=g) * (0.002 + env_s) * 0.25
+    n_frames = int(round(n_samples * 49.95 / 16000))
+    centers = ((torch.arange(n_frames).double() + 0.5) * 16000 / 49.95).long().clamp_(0, n_samples - 1)
+    return x.clamp_(-0.999, 0.999), (env[centers] > 0).numpy()
