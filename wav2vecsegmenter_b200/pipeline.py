@@ -15,6 +15,7 @@ the device is free to batch / shard windows any other way.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -137,6 +138,58 @@ def shard_ranges(n: int, world: int):
     return out
 
 
+class LazyWave:
+    """Device copy of one talk's samples, uploaded in chunks on a side stream just AHEAD of the device
+    batches that read them, so that the host->device copy of a long talk overlaps its own forward
+    passes (the reference copies batch by batch with blocking `.to(device)`, lib/evaluate.py:36-44;
+    a single up-front copy of a 2 h talk is 460 MB). `lo` = first sample this rank needs."""
+
+    # samples per copy (17.9 MB = one 14-window batch); W2VSEG_UPLOAD_CHUNK overrides it for A/B
+    # measurements (a huge value = the whole talk in one copy before the first batch)
+    CHUNK = int(os.environ.get("W2VSEG_UPLOAD_CHUNK", 14 * 320_000))
+
+    def __init__(self, host_wave, device, side, buf=None, lo: int = 0):
+        import torch
+
+        self.host = torch.from_numpy(np.ascontiguousarray(host_wave, dtype=np.float32))
+        self.n = self.host.numel()
+        self.side = side
+        with torch.cuda.stream(side):
+            if buf is None or buf.numel() < self.n:
+                buf = torch.empty(max(self.n, 1), dtype=torch.float32, device=device)
+        self.buf = buf
+        self.dev = buf[: self.n]
+        self.hi = min(max(int(lo), 0), self.n)   # samples [lo, hi) are enqueued
+        self.waited = self.hi                    # ... and [lo, waited) are ordered before the main stream
+        self.events = []                         # (hi after the chunk, event), stream order
+
+    def upload_to(self, upto: int) -> None:
+        """enqueue copies (side stream) until sample `upto` is covered; does not touch the main stream"""
+        import torch
+
+        upto = min(int(upto), self.n)
+        with torch.cuda.stream(self.side):
+            while self.hi < upto:
+                e = min(self.hi + self.CHUNK, self.n)
+                self.dev[self.hi: e].copy_(self.host[self.hi: e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+                self.hi = e
+                self.events.append((e, ev))
+
+    def wait(self, upto: int, main) -> None:
+        """make the main stream wait until samples below `upto` have arrived"""
+        upto = min(int(upto), self.n)
+        if upto <= self.waited:
+            return
+        self.upload_to(upto)
+        while self.events and self.events[0][0] < upto:
+            self.events.pop(0)
+        hi, ev = self.events[0]
+        main.wait_event(ev)
+        self.waited = hi
+
+
 @dataclass
 class TalkResult:
     probs: np.ndarray                 # averaged over tilings, float64 [n_frames]
@@ -177,8 +230,24 @@ class TalkRunner:
         eng = self.engine
         rows = torch.empty(len(wins), r_max + 1, dtype=torch.float32, device=eng.device)
         flags = torch.empty(len(wins), dtype=torch.int32, device=eng.device)
-        for b0 in range(0, len(wins), self.device_batch):
-            group = wins[b0: b0 + self.device_batch]
+        main = torch.cuda.current_stream(eng.device)
+
+        def need(group):   # per talk: one past the last sample the device batch reads
+            out = {}
+            for w in group:
+                out[w.talk] = max(out.get(w.talk, 0), w.end)
+            if len({w.talk for w in group}) == 1 and len(group) > 1:   # strided view runs to a full last row
+                lm = max(w.n_samples for w in group)
+                out[group[0].talk] = max(out[group[0].talk],
+                                         min(group[0].start + (len(group) - 1) * (group[1].start - group[0].start) + lm,
+                                             waves_dev[group[0].talk].n))
+            return out
+
+        groups = [wins[b0: b0 + self.device_batch] for b0 in range(0, len(wins), self.device_batch)]
+        for gi, b0 in enumerate(range(0, len(wins), self.device_batch)):
+            group = groups[gi]
+            for t, upto in need(group).items():
+                waves_dev[t].wait(upto, main)
             lmax = max(w.n_samples for w in group)
             if lmax < 400:
                 rows[b0: b0 + len(group)].zero_()
@@ -188,15 +257,15 @@ class TalkRunner:
             step = group[1].start - first.start if len(group) > 1 else lmax
             regular = (all(w.talk == first.talk for w in group) and step >= lmax
                        and all(w.start == first.start + k * step for k, w in enumerate(group))
-                       and first.start + (len(group) - 1) * step + lmax <= waves_dev[first.talk].numel())
+                       and first.start + (len(group) - 1) * step + lmax <= waves_dev[first.talk].n)
             if regular:
                 # consecutive windows of one talk: a strided VIEW of the talk's samples is the batch
                 # (rows may run past a short last window: sample_len masks that)
-                stage = waves_dev[first.talk].as_strided((len(group), lmax), (step, 1), first.start)
+                stage = waves_dev[first.talk].dev.as_strided((len(group), lmax), (step, 1), first.start)
             else:
                 stage = torch.zeros(len(group), lmax, dtype=torch.float32, device=eng.device)
                 for k, w in enumerate(group):
-                    stage[k, : w.n_samples] = waves_dev[w.talk][w.start: w.end]
+                    stage[k, : w.n_samples] = waves_dev[w.talk].dev[w.start: w.end]
             meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
                                  [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
             R = eng.frame_stride(lmax)
@@ -206,8 +275,19 @@ class TalkRunner:
             rows[b0: b0 + len(group), :R] = probs
             if R < r_max:
                 rows[b0: b0 + len(group), R:r_max].zero_()
+            if gi + 1 < len(groups):   # the next batch's samples travel while this one computes
+                for t, upto in need(groups[gi + 1]).items():
+                    waves_dev[t].upload_to(upto)
         rows[:, r_max] = flags.to(torch.float32)
         return rows
+
+    def _side(self):
+        import torch
+
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(self.engine.device)
+        return side
 
     def _logits_scratch(self, b: int, r: int):
         import torch
@@ -231,12 +311,16 @@ class TalkRunner:
 
             world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
         lo, hi = shard_ranges(len(wins), world)[rank]
+        side = self._side()
+        side.wait_stream(torch.cuda.current_stream(eng.device))
         waves_dev = {}
         for w in wins[lo:hi]:
-            if w.talk not in waves_dev:
-                waves_dev[w.talk] = torch.from_numpy(np.ascontiguousarray(waves[w.talk], dtype=np.float32)).to(
-                    eng.device, non_blocking=True)
+            if w.talk not in waves_dev:   # windows are talk-major, tiling-major: the first one starts lowest
+                first = min(x.start for x in wins[lo:hi] if x.talk == w.talk)
+                waves_dev[w.talk] = LazyWave(waves[w.talk], eng.device, side, lo=first)
         rows = self._forward_rows(waves_dev, wins[lo:hi], r_max)
+        for lw in waves_dev.values():
+            lw.buf.record_stream(torch.cuda.current_stream(eng.device))
         if world > 1:
             rows = gather_rows(rows, len(wins), world, self.dist_group)
         return self.reduce(rows, wins, n_frames)
@@ -277,9 +361,10 @@ class TalkRunner:
 
         eng = self.engine
         main = torch.cuda.current_stream(eng.device)
-        side = getattr(self, "_side_stream", None)
-        if side is None:
-            side = self._side_stream = torch.cuda.Stream(eng.device)
+        side = self._side()
+        down = getattr(self, "_down_stream", None)
+        if down is None:
+            down = self._down_stream = torch.cuda.Stream(eng.device)
         inflight = []      # (done_event, avg_host, tilings_host)
         slots = [None] * depth   # device wave buffers + the event after which they may be overwritten
 
@@ -290,20 +375,7 @@ class TalkRunner:
 
         for k, wave in enumerate(talks):
             wave = np.ascontiguousarray(wave, dtype=np.float32)
-            host = torch.from_numpy(wave)
             slot = k % depth
-            with torch.cuda.stream(side):
-                if slots[slot] is not None:
-                    side.wait_event(slots[slot][1])          # forward of talk k-depth has consumed the buffer
-                if slots[slot] is None or slots[slot][0].numel() < host.numel():
-                    buf = torch.empty(host.numel(), dtype=torch.float32, device=eng.device)
-                else:
-                    buf = slots[slot][0]
-                dev = buf[: host.numel()]
-                dev.copy_(host, non_blocking=True)
-                h2d = torch.cuda.Event()
-                h2d.record(side)
-            main.wait_event(h2d)
             wins, n_frames = self.plan([wave])
             r_max = max([eng.frame_stride(max(w.n_samples, 400)) for w in wins] + [1])
             world, rank = 1, 0
@@ -312,23 +384,31 @@ class TalkRunner:
 
                 world, rank = dist.get_world_size(self.dist_group), dist.get_rank(self.dist_group)
             lo, hi = shard_ranges(len(wins), world)[rank]
-            rows = self._forward_rows({0: dev}, wins[lo:hi], r_max)
+            if slots[slot] is not None:
+                side.wait_event(slots[slot][1])              # forward of talk k-depth has consumed the buffer
+            first = min([w.start for w in wins[lo:hi]] + [len(wave)])
+            lw = LazyWave(wave, eng.device, side, buf=slots[slot][0] if slots[slot] is not None else None, lo=first)
+            lw.upload_to(first + 2 * LazyWave.CHUNK)         # the rest follows batch by batch (_forward_rows)
+            buf = lw.buf
+            rows = self._forward_rows({0: lw}, wins[lo:hi], r_max)
             if world > 1:
                 rows = gather_rows(rows, len(wins), world, self.dist_group)
             avg, til = self.reduce_device(rows, wins, n_frames)[0]
             fwd = torch.cuda.Event()
             fwd.record(main)
             slots[slot] = (buf, fwd)
-            with torch.cuda.stream(side):
-                side.wait_event(fwd)
+            # results leave on their OWN stream: on the upload stream the wait for this forward would
+            # hold back the next talk's host->device copies until the forward has finished
+            with torch.cuda.stream(down):
+                down.wait_event(fwd)
                 avg_h = torch.empty(avg.shape, dtype=avg.dtype, pin_memory=True)
                 til_h = torch.empty(til.shape, dtype=til.dtype, pin_memory=True)
                 avg_h.copy_(avg, non_blocking=True)
                 til_h.copy_(til, non_blocking=True)
-                avg.record_stream(side)
-                til.record_stream(side)
+                avg.record_stream(down)
+                til.record_stream(down)
                 d2h = torch.cuda.Event()
-                d2h.record(side)
+                d2h.record(down)
             inflight.append((d2h, avg_h, til_h))
             if len(inflight) >= depth:
                 yield finish(inflight.pop(0))
