@@ -291,7 +291,7 @@ def run_native(args):
                 v["hbm_frac"] = round(v["hbm_gbs"] / peaks["hbm_gbs"], 3)
             v["ms_per_step"] = round(v["ms_per_step"], 4)
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline = cpu_reference_timing(n_windows=1, reps=2)
+            cpu_baseline = cpu_reference_timing(n_windows=4, reps=2)   # ~10-15 s of CPU work
 
     if rank == 0:
         line = {
@@ -365,7 +365,7 @@ def run_reference(args):
     spec = synth.LARGE_ALL
     sd = synth.random_state_dict(spec, seed=0)
     g = torch.Generator().manual_seed(99)
-    n_win = 1  # bounded sample: 1 of the 14 windows of a batch per step
+    n_win = 2  # bounded sample: 2 of the 14 windows of a batch per step (~15 s for 8 steps on 16 cores)
     audio = sfc_oracle.normalize_rows(torch.randn(n_win, WIN_SAMPLES, generator=g), [True] * n_win)
     out_mask = torch.ones(n_win, T_FRAMES, dtype=torch.bool)
     steps = min(args.steps, 8)
