@@ -32,13 +32,18 @@ def timed(fn, n=20):
 print(f"run() total            {timed(lambda: runner.run([talk])):.3f} ms")
 wins, n_frames = runner.plan([talk])
 print(f"plan() host            {timed(lambda: runner.plan([talk])):.3f} ms")
-dev = torch.from_numpy(talk).to(eng.device)
+from wav2vecsegmenter_b200.pipeline import LazyWave  # noqa: E402
+
+dev = LazyWave(talk, eng.device, runner._side())
+dev.upload_to(len(talk))
+torch.cuda.synchronize()
+dev.waited = dev.hi   # resident: nothing left to wait for
 print(f"H2D 17.9 MB            {timed(lambda: torch.from_numpy(talk).to(eng.device, non_blocking=True)):.3f} ms")
 r_max = max(eng.frame_stride(max(w.n_samples, 400)) for w in wins)
 print(f"_forward_rows          {timed(lambda: runner._forward_rows({0: dev}, wins, r_max)):.3f} ms")
 rows = runner._forward_rows({0: dev}, wins, r_max)
 print(f"reduce() (+D2H)        {timed(lambda: runner.reduce(rows, wins, n_frames)):.3f} ms")
-audio = dev.view(14, 320000)
+audio = dev.dev.view(14, 320000)
 lens = torch.full((14,), 320000, dtype=torch.int32, device="cuda")
 ol = torch.full((14,), 999, dtype=torch.int32, device="cuda")
 print(f"sfc_forward (resident) {timed(lambda: eng.sfc_forward(audio, lens, lens, ol, 320000)):.3f} ms")

@@ -222,7 +222,55 @@ class TalkRunner:
                 wins += plan_tiling(dur, self.segment_sec, self.inference_times, i, self.batch_size, t)
         return wins, n_frames
 
-    def _forward_rows(self, waves_dev, wins: list[Window], r_max: int):
+    def _stage_meta(self, shard: list[Window], wins: list[Window], n_frames: list[int], stream=None):
+        """All small integer inputs of a job — per device batch (sample_len | norm_len | out_len) and per
+        (talk, tiling) the scatter plan (start | count | NaN frames) — packed into ONE pinned host array
+        and sent with ONE copy on `stream` (the upload stream), instead of a handful of tiny pageable
+        copies on the compute stream between the forward passes. Returns (event, batch_meta, plans):
+        batch_meta[g] = int32 [3, len(group g)], plans[(talk, tiling)] = (start, count, nan_idx, lo, hi)
+        with wins[lo:hi] the windows of that tiling."""
+        import torch
+
+        eng = self.engine
+        parts, off = [], 0
+        batch_slices, plan_slices = [], {}
+
+        def push(a):
+            nonlocal off
+            a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+            parts.append(a)
+            off += a.size
+            return off - a.size, a.size
+
+        for b0 in range(0, len(shard), self.device_batch):
+            group = shard[b0: b0 + self.device_batch]
+            o, _ = push([[w.n_samples for w in group], [w.norm_len for w in group], [w.out_len for w in group]])
+            batch_slices.append((o, len(group)))
+        k = 0
+        while k < len(wins):   # wins are talk-major, tiling-major: one contiguous run per (talk, tiling)
+            j = k
+            while j < len(wins) and wins[j].talk == wins[k].talk and wins[j].tiling == wins[k].tiling:
+                j += 1
+            st, ct, nan_idx = scatter_plan(wins[k:j], n_frames[wins[k].talk])
+            plan_slices[(wins[k].talk, wins[k].tiling)] = (push(st), push(ct), push(nan_idx), k, j)
+            k = j
+        total = max(off, 1)
+        host = torch.empty(total, dtype=torch.int32, pin_memory=True)
+        if off:
+            host[:off] = torch.from_numpy(np.concatenate(parts))
+        stream = stream or torch.cuda.current_stream(eng.device)
+        with torch.cuda.stream(stream):
+            dev = torch.empty(total, dtype=torch.int32, device=eng.device)
+            dev.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        dev.record_stream(torch.cuda.current_stream(eng.device))
+        batch_meta = [dev[o: o + 3 * n].view(3, n) for o, n in batch_slices]
+        plans = {key: (dev[a[0]: a[0] + a[1]], dev[b[0]: b[0] + b[1]], dev[c[0]: c[0] + c[1]], lo, hi)
+                 for key, (a, b, c, lo, hi) in plan_slices.items()}
+        return ev, batch_meta, plans
+
+    def _forward_rows(self, waves_dev, wins: list[Window], r_max: int, batch_meta=None):
         """probability rows fp32 [len(wins), r_max + 1] on the device for the given windows; the
         last column carries the window's `included` flag (1.0 / 0.0)"""
         import torch
@@ -266,8 +314,11 @@ class TalkRunner:
                 stage = torch.zeros(len(group), lmax, dtype=torch.float32, device=eng.device)
                 for k, w in enumerate(group):
                     stage[k, : w.n_samples] = waves_dev[w.talk].dev[w.start: w.end]
-            meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
-                                 [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
+            if batch_meta is not None:
+                meta = batch_meta[gi]
+            else:
+                meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
+                                     [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
             R = eng.frame_stride(lmax)
             _, probs = eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax,
                                        logits_out=self._logits_scratch(len(group), R),
@@ -318,16 +369,19 @@ class TalkRunner:
             if w.talk not in waves_dev:   # windows are talk-major, tiling-major: the first one starts lowest
                 first = min(x.start for x in wins[lo:hi] if x.talk == w.talk)
                 waves_dev[w.talk] = LazyWave(waves[w.talk], eng.device, side, lo=first)
-        rows = self._forward_rows(waves_dev, wins[lo:hi], r_max)
+        ev, batch_meta, plans = self._stage_meta(wins[lo:hi], wins, n_frames, side)
+        torch.cuda.current_stream(eng.device).wait_event(ev)
+        rows = self._forward_rows(waves_dev, wins[lo:hi], r_max, batch_meta)
         for lw in waves_dev.values():
             lw.buf.record_stream(torch.cuda.current_stream(eng.device))
         if world > 1:
             rows = gather_rows(rows, len(wins), world, self.dist_group)
-        return self.reduce(rows, wins, n_frames)
+        return self.reduce(rows, wins, n_frames, plans)
 
-    def reduce_device(self, rows, wins: list[Window], n_frames: list[int]):
+    def reduce_device(self, rows, wins: list[Window], n_frames: list[int], plans=None):
         """rows [len(wins), r] (device) -> per talk (avg float64 [n], tilings float64 [inference_times, n]) on
-        the device: scatter, NaN fill and tiling average kernels, no host round trip"""
+        the device: scatter, NaN fill and tiling average kernels, no host round trip. `plans` = the
+        scatter plans already on the device (_stage_meta); without it they are computed and sent here."""
         import torch
 
         eng = self.engine
@@ -335,20 +389,24 @@ class TalkRunner:
         for t, n in enumerate(n_frames):
             tilings = torch.empty(self.inference_times, n, dtype=torch.float64, device=eng.device)
             for i in range(self.inference_times):
-                idx = [k for k, w in enumerate(wins) if w.talk == t and w.tiling == i]
-                sub = [wins[k] for k in idx]
-                st, ct, nan_idx = scatter_plan(sub, n)
-                talk_rows = rows[idx[0]: idx[-1] + 1] if idx else rows[:0]
+                if plans is not None and (t, i) in plans:
+                    st, ct, nan_idx, k0, k1 = plans[(t, i)]
+                    talk_rows = rows[k0:k1]
+                else:
+                    idx = [k for k, w in enumerate(wins) if w.talk == t and w.tiling == i]
+                    sub = [wins[k] for k in idx]
+                    st, ct, nan_idx = scatter_plan(sub, n)
+                    talk_rows = rows[idx[0]: idx[-1] + 1] if idx else rows[:0]
                 talk = eng.scatter_rows(talk_rows, st, ct, n, flag_col=talk_rows.shape[1] - 1)
                 eng.nanfill(talk, nan_idx)
                 tilings[i] = talk
             out.append((eng.overlap_average(tilings), tilings))
         return out
 
-    def reduce(self, rows, wins: list[Window], n_frames: list[int]) -> list[TalkResult]:
+    def reduce(self, rows, wins: list[Window], n_frames: list[int], plans=None) -> list[TalkResult]:
         """rows [len(wins), r] (device) -> per-talk averaged probabilities on the host"""
         return [TalkResult(avg.cpu().numpy(), [til[i].cpu().numpy() for i in range(self.inference_times)])
-                for avg, til in self.reduce_device(rows, wins, n_frames)]
+                for avg, til in self.reduce_device(rows, wins, n_frames, plans)]
 
     def run_stream(self, talks, depth: int = 2):
         """Throughput API: yields one TalkResult per input talk (same values as run([wave])[0]), with a
@@ -390,10 +448,12 @@ class TalkRunner:
             lw = LazyWave(wave, eng.device, side, buf=slots[slot][0] if slots[slot] is not None else None, lo=first)
             lw.upload_to(first + 2 * LazyWave.CHUNK)         # the rest follows batch by batch (_forward_rows)
             buf = lw.buf
-            rows = self._forward_rows({0: lw}, wins[lo:hi], r_max)
+            ev, batch_meta, plans = self._stage_meta(wins[lo:hi], wins, n_frames, side)
+            main.wait_event(ev)
+            rows = self._forward_rows({0: lw}, wins[lo:hi], r_max, batch_meta)
             if world > 1:
                 rows = gather_rows(rows, len(wins), world, self.dist_group)
-            avg, til = self.reduce_device(rows, wins, n_frames)[0]
+            avg, til = self.reduce_device(rows, wins, n_frames, plans)[0]
             fwd = torch.cuda.Event()
             fwd.record(main)
             slots[slot] = (buf, fwd)
