@@ -44,8 +44,20 @@ int num_sms() {
   return g_num_sms;
 }
 
+static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw);
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
                       uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
+  return make_tmap_2d_impl(out, base, dim0, dim1, row_stride_elems, box0, box1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                           uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
+  return make_tmap_2d_impl(out, base, dim0, dim1, row_stride_elems, box0, box1, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -69,7 +81,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, box "

@@ -3,6 +3,17 @@
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
+#ifdef W2VSEG_TRACE
+// experiments only (scripts/prof_gemm_trace.py): clock64 stamps of CTA 0, one copy per translation unit
+static __device__ long long g_trace[12 * 64];
+#define W2V_TR(slot, idx)                                                                       \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && lane == 0 && (idx) >= 0 && (idx) < 64) g_trace[(slot) * 64 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define W2V_TR(slot, idx) do { } while (0)
+#endif
+
 namespace w2v {
 
 struct KernelArgs {
@@ -19,15 +30,17 @@ struct KernelArgs {
   int out_f32;
   const int* mask_len;
   int mask_period;
+  int tma_store;   // bf16 output leaves through a TMA store of the staging block (tmap_o valid)
 };
 
 // One epilogue warp, one accumulator tile: rows rg0..rg0+31 (TMEM lane quarter of this warp),
 // COLS columns starting at colbase. `wait_full` is invoked after the residual prefetch has been
 // issued and must block until the accumulator is complete (mbarrier wait + tcgen05 fence).
-template <int COLS, bool OUT_F32, typename WaitFull>
+template <int COLS, bool OUT_F32, int TMA_BUFS = 2, typename WaitFull>
 __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0, long long orow0,
                                                    int colbase, uint32_t t_base, uint32_t stage,
-                                                   int lane, WaitFull&& wait_full) {
+                                                   int lane, WaitFull&& wait_full, int trace_it = -1,
+                                                   const CUtensorMap* tmap_o = nullptr) {
   constexpr int UNIT = OUT_F32 ? 32 : 64;           // columns per staging block (128 B per row)
   static_assert(COLS % UNIT == 0, "bf16 output needs BLOCK_N >= 128");
   constexpr int NUNIT = COLS / UNIT;
@@ -67,6 +80,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
 #pragma unroll
   for (int u = 0; u < NUNIT; ++u) {
     tc_wait_ld();
+    if (u == 0) W2V_TR(6, trace_it);
+    if (u == 1) W2V_TR(8, trace_it);
     if (u + 1 < NUNIT) {
       if constexpr (OUT_F32) {
         if (use_resid) {
@@ -100,9 +115,87 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
 #pragma unroll
       for (int j = 0; j < UNIT; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+#ifdef W2VSEG_EPI_EXPERIMENT
+    else if (act == 3) {   // MUFU only
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[j])); v[j] = t; }
+    } else if (act == 4) {   // 8 FP ops, no MUFU
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) {
+        const float x = v[j];
+        const float x2 = fminf(x * x, 36.f);
+        float p = fmaf(-0.00035854941503117723f, x2, 0.03704889695510829f);
+        p = fmaf(p, x2, 0.7974606740658886f);
+        const float t = p * x;
+        const float hx = 0.5f * x;
+        v[j] = fmaf(hx, t, hx);
+      }
+    } else if (act == 5) {   // 3 FP ops + MUFU
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) {
+        const float x = v[j];
+        float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * 0.79f));
+        const float hx = 0.5f * x;
+        v[j] = fmaf(hx, t, hx);
+      }
+    }
+#endif
     if (zero_row) {
 #pragma unroll
       for (int j = 0; j < UNIT; ++j) v[j] = 0.f;
+    }
+#ifdef W2VSEG_TRACE
+    {   // keep the math above the stamp: consume one value through a volatile asm
+      asm volatile("" ::"f"(v[UNIT - 1]), "f"(v[0]));
+      if (u == 0) W2V_TR(9, trace_it);
+      if (u == 1) W2V_TR(10, trace_it);
+    }
+#endif
+    // bf16 output through TMA (tmap_o): the 64-column block leaves as TWO 32-row x 32-column boxes
+    // (64-byte rows, 64-byte swizzle), each from its own 2 KB half of the staging buffer, so the warp
+    // never waits for the store it has just issued: before a half is overwritten only the store issued
+    // from it one block earlier must have been read (wait_group.read 1). The coalescing loop below
+    // (8 x LDS.128 + STG.128 per block) held the warp ~2400 cycles per block under load — the SM's store
+    // path drains at ~10 B/clk while the operand loads run — which made the epilogue, not the MMAs, set
+    // the pace of the GEMMs with an activation.
+    bool via_tma = false;
+    if constexpr (!OUT_F32) via_tma = tmap_o != nullptr;
+    if constexpr (!OUT_F32) {
+      if (via_tma) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          // TMA_BUFS 2 KB buffers per warp, used round-robin (NUNIT * 2 blocks per tile is a multiple of
+          // TMA_BUFS): before one is overwritten, all but the TMA_BUFS-1 newest stores must have been read
+          const uint32_t buf = stage + (uint32_t)(((u * 2 + hb) % TMA_BUFS) * 2048);
+          if (lane == 0) {
+            if constexpr (TMA_BUFS == 4) bulk_wait_group_read3(); else bulk_wait_group_read1();
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = hb * 32 + c * 8;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                             buf + (uint32_t)(lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4))),
+                         "r"(pack_bf16x2(v[j + 0], v[j + 1])), "r"(pack_bf16x2(v[j + 2], v[j + 3])),
+                         "r"(pack_bf16x2(v[j + 4], v[j + 5])), "r"(pack_bf16x2(v[j + 6], v[j + 7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();   // staging writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmap_o, buf, col0 + hb * 32, (int)orow0);   // rows past the end are clipped
+            bulk_commit_group();
+          }
+        }
+        if (u + 1 < NUNIT) {   // v[] is dead: fetch the next block (TMEM load latency is ~60 cycles)
+#pragma unroll
+          for (int l = 0; l < LPU; ++l)
+            tmem_ld_32x32b_x32(t_base + (uint32_t)((u + 1) * UNIT + l * 32),
+                               *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
+        }
+        if (u == 0) W2V_TR(7, trace_it);
+        continue;
+      }
     }
     // row-per-thread -> staging (row = lane, 8 chunks of 16 B, chunk index XOR row%8)
     const uint32_t srow = stage + (uint32_t)(lane * 128);
@@ -127,6 +220,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
                            *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
     }
     __syncwarp();
+    if (u == 0) W2V_TR(7, trace_it);
     // staging -> global, coalesced: 4 rows x 128 B per warp instruction
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

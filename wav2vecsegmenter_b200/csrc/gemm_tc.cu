@@ -188,6 +188,7 @@ int launch_impl(const GemmProblem& g, cudaStream_t stream) {
   W2V_TRY(make_tmap_2d_bf16(&tm_b, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BLOCK_K,
                             BLOCK_N));
   KernelArgs a;
+  a.tma_store = 0;
   a.N = g.N; a.K = g.K;
   a.num_groups = g.num_groups;
   a.rows_per_group = g.rows_per_group;

@@ -10,6 +10,8 @@
 // Roles per CTA (10 warps): warp 0 TMA producer (own A rows + own W half, completion credited to
 // the leader's mbarrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs),
 // warps 2..9 epilogue (each CTA drains its own 128 accumulator rows; TMEM double-buffered).
+#include <stdlib.h>
+
 #include "gemm_epilogue.cuh"
 
 namespace w2v {
@@ -25,21 +27,28 @@ constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = HALF_N * BLOCK_K * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STAGES = 6;
+#ifndef W2V_PAIR_STAGES
+#define W2V_PAIR_STAGES 6
+#endif
+constexpr int STAGES = W2V_PAIR_STAGES;
+constexpr int STAGE_BUF = STAGES == 6 ? 4096 : 8192;   // epilogue staging per warp (5 stages free 32 KB)
+constexpr int TMA_BUFS = STAGE_BUF / 2048;
 constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumulators
 constexpr int THREADS = 320;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * STAGE_BUF;
 
 template <bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const KernelArgs p) {
+                const __grid_constant__ CUtensorMap tmap_o, const KernelArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // epilogue staging (8 x 4 KB, 1024-byte aligned: a staging block doubles as a swizzled TMA box)
+  uint8_t* smem_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + 8 * STAGE_BUF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] (only the leader's copy is used)
@@ -59,6 +68,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_o);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -111,8 +121,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        W2V_TR(3, it);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        W2V_TR(4, it);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -132,6 +145,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        W2V_TR(5, it);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -141,10 +155,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int COLS = BLOCK_N / 2;
-    const uint32_t stage_buf = smem_u32(smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * 4096);
+    const uint32_t stage_buf = smem_u32(smem_stage + (warp - 2) * STAGE_BUF);
+    const CUtensorMap* tm_o = p.tma_store ? &tmap_o : nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int nb = tile % n_tiles;
       const int mt = tile / n_tiles;
       const int g = mt / p.tiles_m_per_group;
@@ -153,17 +169,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const long long orow0 = (long long)g * p.o_group_rows + rg0;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)(acc * BLOCK_N + half * COLS);
-      gemm_epilogue_warp<COLS, OUT_F32>(p, rg0, orow0, nb * BLOCK_N + half * COLS, t_base, stage_buf,
+      gemm_epilogue_warp<COLS, OUT_F32, TMA_BUFS>(p, rg0, orow0, nb * BLOCK_N + half * COLS, t_base, stage_buf,
                                         lane, [&] {
+                                          if (warp == 2) W2V_TR(0, it);
                                           mbar_wait(&tfull_bar[acc], acc_phase);
+                                          if (warp == 2) W2V_TR(1, it);
                                           tc_fence_after();
-                                        });
+                                        }, warp == 2 ? it : -1, tm_o);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the leader's MMA thread waits here
+      if (warp == 2) W2V_TR(2, it);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (tm_o != nullptr && lane == 0) bulk_wait_group_read0();   // staging must outlive the last store's read
   }
 
   tc_fence_before();
@@ -188,7 +208,16 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   W2V_TRY(make_tmap_2d_bf16(&tm_a, g.A, (uint64_t)g.a_cols, (uint64_t)g.a_rows,
                             (uint64_t)g.a_row_stride, BLOCK_K, BLOCK_M));
   W2V_TRY(make_tmap_2d_bf16(&tm_b, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BLOCK_K, HALF_N));
+  // bf16 output of a flat problem leaves through TMA stores (32-row x 32-column boxes, 64-byte swizzle)
+  static const bool tma_allowed = !(getenv("W2VSEG_GEMM_TMA_STORE") != nullptr &&
+                                    atoi(getenv("W2VSEG_GEMM_TMA_STORE")) == 0);   // =0: A/B measurements
+  const bool tma_out = tma_allowed && !g.out_f32 && g.num_groups == 1 &&
+                       (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && g.ld_out % 8 == 0;
+  CUtensorMap tm_o = tm_a;
+  if (tma_out)
+    W2V_TRY(make_tmap_2d_bf16_sw64(&tm_o, g.out, (uint64_t)g.N, (uint64_t)g.rows_per_group, (uint64_t)g.ld_out, 32, 32));
   KernelArgs a;
+  a.tma_store = tma_out ? 1 : 0;
   a.N = g.N; a.K = g.K;
   a.num_groups = g.num_groups;
   a.rows_per_group = g.rows_per_group;
@@ -215,12 +244,18 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   {
     ProfScope ps(stream, "gemm_pair256");
     if (g.out_f32)
-      gemm_tc2_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+      gemm_tc2_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
     else
-      gemm_tc2_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, a);
+      gemm_tc2_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
   }
   W2V_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace w2v
+
+#ifdef W2VSEG_TRACE
+extern "C" int32_t w2vseg_debug_trace(long long* host_dst, int32_t n) {
+  return (int32_t)cudaMemcpyFromSymbol(host_dst, g_trace, sizeof(long long) * (size_t)(n < 768 ? n : 768));
+}
+#endif

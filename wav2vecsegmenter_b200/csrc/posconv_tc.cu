@@ -216,6 +216,7 @@ int posconv_tc_launch(const GemmProblem& g, cudaStream_t stream) {
                             PC_BK, PC_BM));
   W2V_TRY(make_tmap_2d_bf16(&tm_b, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, PC_BK, PC_BN));
   KernelArgs a;
+  a.tma_store = 0;
   a.N = g.N; a.K = g.K;
   a.num_groups = g.num_groups;
   a.rows_per_group = g.rows_per_group;

@@ -102,8 +102,20 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_read3() {
+  asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_read1() {   // all but the newest committed group read
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_group_read0() {   // sources of all committed groups read
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -233,13 +245,18 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.
+// Default semantics (.release at CTA scope), NOT .release.cluster: a cluster-scope release has to
+// drain the thread's outstanding global stores first — measured ~3000 cycles per accumulator
+// hand-over in the GEMM epilogue (scripts/prof_gemm_trace.py), which made the epilogue as long as
+// the mainloop. The barrier only orders TMEM reads (tcgen05.wait::ld + fence::before_thread_sync)
+// against the next MMAs; no generic-memory data is published through it.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n"
       :
       : "r"(smem_u32(bar)), "r"(rank)
