@@ -45,11 +45,16 @@ int num_sms() {
 }
 
 static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
-                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw);
+                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw,
+                             int elem_bytes = 2);
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
                       uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
   return make_tmap_2d_impl(out, base, dim0, dim1, row_stride_elems, box0, box1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                     uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
+  return make_tmap_2d_impl(out, base, dim0, dim1, row_stride_elems, box0, box1, CU_TENSOR_MAP_SWIZZLE_128B, 4);
 }
 int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
                            uint64_t row_stride_elems, uint32_t box0, uint32_t box1) {
@@ -57,7 +62,8 @@ int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t dim0, ui
 }
 
 static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
-                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw) {
+                             uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw,
+                             int elem_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -70,16 +76,17 @@ static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, 
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return W2VSEG_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * elem_bytes) % 16 != 0) {
     set_error("tensor map: base %p / row stride %llu not 16-byte aligned", base,
               (unsigned long long)row_stride_elems);
     return W2VSEG_ERR_ARG;
   }
   cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {row_stride_elems * 2};  // bytes, dim1 stride
+  cuuint64_t gstride[1] = {row_stride_elems * (uint64_t)elem_bytes};  // bytes, dim1 stride
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                        2, const_cast<void*>(base), gdim,
                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

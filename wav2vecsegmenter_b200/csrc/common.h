@@ -61,6 +61,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
 int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
                            uint64_t row_stride_elems, uint32_t box0, uint32_t box1);
 
+// fp32 elements, 128-byte swizzle (the residual GEMMs' 32 x 32 reduce-add boxes)
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
+                     uint64_t row_stride_elems, uint32_t box0, uint32_t box1);
+
 // 3-D variant (box = box0 x box1 x 1): the third dimension isolates planes (e.g. windows) so that a
 // box hanging over the end of one plane is clipped instead of spilling into the next one.
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,

@@ -197,6 +197,15 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
         continue;
       }
     }
+    // in-place fp32 residual through TMA (tmap_o): the 32 x 32 fp32 staging block (128-byte rows, the
+    // XOR pattern below IS the 128-byte TMA swizzle) goes out as ONE bulk reduce-add (h += block at L2)
+    // instead of 8 x (LDS.128 + RED.v4) per thread
+    bool red_tma = false;
+    if constexpr (OUT_F32) red_tma = use_red && tmap_o != nullptr;
+    if (red_tma) {   // the previous block's reduction must have finished READING the staging buffer
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+    }
     // row-per-thread -> staging (row = lane, 8 chunks of 16 B, chunk index XOR row%8)
     const uint32_t srow = stage + (uint32_t)(lane * 128);
 #pragma unroll
@@ -218,6 +227,16 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
       for (int l = 0; l < LPU; ++l)
         tmem_ld_32x32b_x32(t_base + (uint32_t)((u + 1) * UNIT + l * 32),
                            *reinterpret_cast<uint32_t(*)[32]>(&raw[l * 32]));
+    }
+    if (red_tma) {
+      fence_proxy_async_smem();   // staging writes -> visible to the async proxy
+      __syncwarp();
+      if (u == 0) W2V_TR(7, trace_it);
+      if (lane == 0) {
+        tma_reduce_add_2d(tmap_o, stage, col0, (int)orow0);   // rows past the end are clipped
+        bulk_commit_group();
+      }
+      continue;
     }
     __syncwarp();
     if (u == 0) W2V_TR(7, trace_it);

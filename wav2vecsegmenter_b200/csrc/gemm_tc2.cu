@@ -216,8 +216,14 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   CUtensorMap tm_o = tm_a;
   if (tma_out)
     W2V_TRY(make_tmap_2d_bf16_sw64(&tm_o, g.out, (uint64_t)g.N, (uint64_t)g.rows_per_group, (uint64_t)g.ld_out, 32, 32));
+  // ... and the in-place fp32 residual (h += acc + bias) through TMA reduce-adds (32 x 32 fp32 boxes)
+  const bool tma_red = tma_allowed && g.out_f32 && g.num_groups == 1 && g.resid != nullptr &&
+                       g.resid == g.out && g.ld_resid == g.ld_out && g.mask_len == nullptr &&
+                       (reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && g.ld_out % 4 == 0;
+  if (tma_red)
+    W2V_TRY(make_tmap_2d_f32(&tm_o, g.out, (uint64_t)g.N, (uint64_t)g.rows_per_group, (uint64_t)g.ld_out, 32, 32));
   KernelArgs a;
-  a.tma_store = tma_out ? 1 : 0;
+  a.tma_store = (tma_out || tma_red) ? 1 : 0;
   a.N = g.N; a.K = g.K;
   a.num_groups = g.num_groups;
   a.rows_per_group = g.rows_per_group;

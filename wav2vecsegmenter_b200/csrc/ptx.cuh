@@ -108,6 +108,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
                "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// shared -> global tile REDUCTION (element-wise += at L2; element type from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
