@@ -9,7 +9,11 @@
 //
 // Roles per CTA (10 warps): warp 0 TMA producer (own A rows + own W half, completion credited to
 // the leader's mbarrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs),
-// warps 2..9 epilogue (each CTA drains its own 128 accumulator rows; TMEM double-buffered).
+// warps 2..9 epilogue (each CTA drains its own 128 accumulator rows; TMEM double-buffered). The epilogue
+// leaves through the TMA engine (bf16: cp.async.bulk.tensor stores of swizzled 32 x 32 boxes; in-place
+// fp32 residual: cp.reduce.async.bulk.tensor .add of 32 x 32 fp32 boxes) and hands the accumulator back
+// with a CTA-scope-release remote arrive — see gemm_epilogue.cuh / ptx.cuh for why (a cluster-scope
+// release there cost ~3000 cycles per tile; profiles/gemm_epilogue_trace_r01_s3.md).
 #include <stdlib.h>
 
 #include "gemm_epilogue.cuh"
