@@ -160,14 +160,41 @@ def run_native(args):
     R = eng.frame_stride(WIN_SAMPLES)
     logits = torch.empty(BATCH, R, device=dev)
     probs = torch.empty(BATCH, R, device=dev)
-    gathered = torch.empty(world * BATCH, R, device=dev) if world > 1 else None
+    # N > 1: the path's only exchange (per-frame probability rows to every rank) runs on its own
+    # stream, double-buffered, so the gather of step i overlaps the forward of step i+1 and the ranks
+    # are not re-synchronised by a collective between every two steps (the timed region still ends
+    # only when the last gather has completed on every rank).
+    serial_gather = os.environ.get("W2VSEG_BENCH_SERIAL_GATHER") == "1"   # A/B: gather on the compute stream
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    probs2 = [probs, torch.empty_like(probs)]
+    gathered2 = [torch.empty(world * BATCH, R, device=dev) for _ in range(2)] if world > 1 else None
+    gather_done = [None, None]
 
     def step(i):
-        eng.sfc_forward(audio[i % n_rot], lens, lens, out_len, WIN_SAMPLES, logits, probs)
-        if world > 1:  # the path's only exchange: per-frame probability rows to every rank
-            dist.all_gather_into_tensor(gathered, probs)
+        k = i & 1
+        main = torch.cuda.current_stream(dev)
+        if world > 1 and gather_done[k] is not None:
+            main.wait_event(gather_done[k])          # the gather that read probs2[k] two steps ago
+        eng.sfc_forward(audio[i % n_rot], lens, lens, out_len, WIN_SAMPLES, logits, probs2[k])
+        if world > 1:
+            fwd = torch.cuda.Event()
+            fwd.record(main)
+            if serial_gather:
+                dist.all_gather_into_tensor(gathered2[k], probs2[k])
+                return
+            with torch.cuda.stream(comm):
+                comm.wait_event(fwd)
+                dist.all_gather_into_tensor(gathered2[k], probs2[k])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            gather_done[k] = ev
+
+    def drain():
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(comm)
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -189,6 +216,7 @@ def run_native(args):
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()      # the last gathers are inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
