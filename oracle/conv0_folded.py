@@ -43,6 +43,7 @@ def forward(x: np.ndarray, rows_f16: np.ndarray, U: np.ndarray, eps: float = 1e-
     s = z @ U.T.astype(np.float32)                                            # rows of U z
     var = np.sum(s * s, axis=1, dtype=np.float32)
     rstd = (1.0 / np.sqrt(var + np.float32(eps))).astype(np.float32)
-    a = np.concatenate([frames * rstd[:, None], rstd[:, None], np.ones((T, 1), np.float32)], axis=1)
+    a = np.concatenate([np.clip(frames * rstd[:, None], -60000.0, 60000.0), rstd[:, None],
+                        np.ones((T, 1), np.float32)], axis=1)   # clip = the kernel's fp16 range guard
     a16 = a.astype(np.float16)
     return a16.astype(np.float32) @ rows_f16.astype(np.float32).T            # fp32 accumulate

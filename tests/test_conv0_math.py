@@ -52,3 +52,20 @@ def test_variance_is_a_sum_of_squares():
     y = w.astype(np.float64) @ x + b
     z = np.concatenate([x, [1.0]])
     assert abs(np.sum((U.astype(np.float64) @ z) ** 2) - y.var()) < 1e-5 * y.var()
+
+
+def test_fp16_range_guard_on_a_dead_tap():
+    """a huge sample along a direction the taps ignore must not turn the frame into NaNs (inf * 0)"""
+    rng = np.random.default_rng(11)
+    w = (rng.standard_normal((512, 10)) * 0.4).astype(np.float32)
+    w[:, 3] = 0.0
+    b = np.full(512, 0.1, np.float32)
+    gamma = np.ones(512, np.float32)
+    beta = np.zeros(512, np.float32)
+    x = np.zeros(400, np.float32)
+    x[3::5] = 1000.0                     # only tap 3 (and 8) of each frame see it; tap 8 is live
+    x[8::5] = 0.0
+    x[3] = 5e4
+    rows, U = conv0_folded.pack(w, b, gamma, beta)
+    got = conv0_folded.forward(x, rows, U)
+    assert np.isfinite(got).all()

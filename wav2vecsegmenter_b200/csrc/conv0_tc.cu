@@ -238,12 +238,16 @@ conv0_tc_kernel(const float* __restrict__ audio, long long audio_stride,
           var = fmaf(s, s, var);
         }
         const float rstd = rsqrtf(var + eps);
+        // fp16 range guard: rstd * x can only leave it when x is huge along a direction the taps ignore
+        // (a tap no channel uses); unclamped, inf * 0 would turn the frame into NaNs
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xv[k] = fminf(fmaxf(xv[k] * rstd, -60000.f), 60000.f);
         uint4 c0, c1;
-        c0.x = pack_half2(xv[0] * rstd, xv[1] * rstd);
-        c0.y = pack_half2(xv[2] * rstd, xv[3] * rstd);
-        c0.z = pack_half2(xv[4] * rstd, xv[5] * rstd);
-        c0.w = pack_half2(xv[6] * rstd, xv[7] * rstd);
-        c1.x = pack_half2(xv[8] * rstd, xv[9] * rstd);
+        c0.x = pack_half2(xv[0], xv[1]);
+        c0.y = pack_half2(xv[2], xv[3]);
+        c0.z = pack_half2(xv[4], xv[5]);
+        c0.w = pack_half2(xv[6], xv[7]);
+        c1.x = pack_half2(xv[8], xv[9]);
         c1.y = pack_half2(rstd, 1.f);
         c1.z = 0u;
         c1.w = 0u;
