@@ -33,19 +33,28 @@ class _EngineHolder:
         self.pending: dict = {}
         self.dirty = False
 
-    def ensure(self, device=None) -> SFCEngine:
+    def create(self, device=None) -> SFCEngine:
+        """engine (device arena, no weights yet). `.to(device)` stops here: the reference moves the
+        module BEFORE it loads the checkpoint (segment.py:41-51), so with a frozen encoder the head
+        weights are still missing at this point."""
         if self.engine is None:
             dev = torch.device(device if device is not None else "cuda:0")
             if dev.type != "cuda":
                 raise RuntimeError("lib.models.SHAS (B200 build) runs on CUDA only: there is no CPU path")
             self.engine = SFCEngine(self.spec, dev)
             self.dirty = True
-        if self.dirty and self.pending:
-            self.engine.load_encoder_state(self.pending, "wav2vec_model.model.")
-            self.engine.load_head_state(self.pending, "seg_model.")
-            self.engine.finalize()
-            self.dirty = False
         return self.engine
+
+    def ensure(self, device=None) -> SFCEngine:
+        """engine with every pending weight uploaded and finalised: called by the first forward /
+        `.engine` access, i.e. after load_state_dict. Missing tensors surface here (W2VSegError)."""
+        eng = self.create(device)
+        if self.dirty:
+            eng.load_encoder_state(self.pending, "wav2vec_model.model.")
+            eng.load_head_state(self.pending, "seg_model.")
+            eng.finalize()
+            self.dirty = False
+        return eng
 
 
 def _pretrained_encoder_state(name: str, spec: ModelSpec) -> dict:
@@ -126,7 +135,7 @@ class SHAS(nn.Module):
 
     def to(self, device=None, *args, **kwargs):
         if device is not None and torch.device(device).type == "cuda":
-            self._holder.ensure(device)
+            self._holder.create(device)
         elif device is not None:
             raise RuntimeError("lib.models.SHAS (B200 build) runs on CUDA only: there is no CPU path")
         return self

@@ -136,18 +136,44 @@ __device__ long long g_ep[8];
 #endif
 
 // One work item = (window b, head, 128-row query tile). A CTA walks items blockIdx.x, +gridDim.x, ...
+// Item coordinates advance by a host-precomputed (qt, head, b) step with carries: an integer division
+// per item change costs ~1500 cycles here, because I2F / MUFU.RCP / F2I queue behind the exponentials
+// on the XU pipe (clock64 timeline, profiles/attention_experiments_r02.md).
 struct Item {
   int q0, head, b, klen, n_tiles, row_base;
 };
+struct Step {
+  int qt, head, b;      // idx -> (qt, head, b) decomposition of the grid stride
+};
+struct Pos {
+  int idx, qt, head, b;
+};
+__device__ __forceinline__ Pos pos_first(int idx, int n_qt, int heads) {
+  Pos p;
+  p.idx = idx;
+  p.qt = idx % n_qt;
+  const int bh = idx / n_qt;
+  p.head = bh % heads;
+  p.b = bh / heads;
+  return p;
+}
+__device__ __forceinline__ void pos_advance(Pos& p, const Step& st, int stride, int n_qt, int heads) {
+  p.idx += stride;
+  p.qt += st.qt;
+  int c = 0;
+  if (p.qt >= n_qt) { p.qt -= n_qt; c = 1; }
+  p.head += st.head + c;
+  c = 0;
+  if (p.head >= heads) { p.head -= heads; c = 1; }
+  p.b += st.b + c;
+}
 // kv_len points at the CTA's shared-memory copy of the (clamped) key lengths: a global load here
 // sits on the critical path of every item change (~2000 cycles under the TMA traffic, measured)
-__device__ __forceinline__ Item make_item(int idx, int n_qt, int heads, int R, const int* kv_len) {
+__device__ __forceinline__ Item make_item(const Pos& p, int R, const int* kv_len) {
   Item it;
-  const int qt = idx % n_qt;
-  const int bh = idx / n_qt;
-  it.head = bh % heads;
-  it.b = bh / heads;
-  it.q0 = qt * A6_BM;
+  it.head = p.head;
+  it.b = p.b;
+  it.q0 = p.qt * A6_BM;
   it.klen = kv_len[it.b];
   it.n_tiles = (it.klen + A6_BN - 1) / A6_BN;
   it.row_base = it.b * R;
@@ -155,31 +181,34 @@ __device__ __forceinline__ Item make_item(int idx, int n_qt, int heads, int R, c
 }
 // Position in this CTA's stream of key tiles (items with no valid key contribute no tile).
 struct Cursor {
-  int idx;      // item index (>= n_items: end of stream)
+  Pos pos;      // item (pos.idx >= n_items: end of stream)
   int seq;      // number of non-empty items before this one (Q / row-sum buffer parity)
   int j;        // key tile within the item
   Item it;
 };
-__device__ __forceinline__ void cursor_skip_empty(Cursor& c, int n_items, int stride, int n_qt, int heads,
-                                                  int R, const int* kv_len) {
-  while (c.idx < n_items) {
-    c.it = make_item(c.idx, n_qt, heads, R, kv_len);
+struct Walk {
+  int n_items, stride, n_qt, heads, R;
+  Step st;
+  const int* kv_len;
+};
+__device__ __forceinline__ void cursor_skip_empty(Cursor& c, const Walk& w) {
+  while (c.pos.idx < w.n_items) {
+    c.it = make_item(c.pos, w.R, w.kv_len);
     if (c.it.n_tiles > 0) return;
-    c.idx += stride;
+    pos_advance(c.pos, w.st, w.stride, w.n_qt, w.heads);
   }
 }
-__device__ __forceinline__ void cursor_next(Cursor& c, int n_items, int stride, int n_qt, int heads, int R,
-                                            const int* kv_len) {
+__device__ __forceinline__ void cursor_next(Cursor& c, const Walk& w) {
   if (++c.j < c.it.n_tiles) return;
   c.j = 0;
   c.seq += 1;
-  c.idx += stride;
-  cursor_skip_empty(c, n_items, stride, n_qt, heads, R, kv_len);
+  pos_advance(c.pos, w.st, w.stride, w.n_qt, w.heads);
+  cursor_skip_empty(c, w);
 }
 
 __global__ void __launch_bounds__(A6_THREADS, 2)
 attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                      int R, int heads, int n_qt, int n_items, int B, const int* __restrict__ kv_len_g,
+                      int R, int heads, int n_qt, int n_items, int B, Step step, const int* __restrict__ kv_len_g,
                       float scale_log2, __nv_bfloat16* __restrict__ ctx) {
   extern __shared__ uint8_t att_raw[];
   uint8_t* smem = att_raw;
@@ -206,6 +235,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   const int D = heads * A6_DH;
   const int stride = gridDim.x;
   int* kv_len = reinterpret_cast<int*>(smem + A6_OFF_KLEN);
+  const Walk walk = {n_items, stride, n_qt, heads, R, step, kv_len};
   for (int i = threadIdx.x; i < B; i += A6_THREADS) kv_len[i] = min(__ldg(kv_len_g + i), R);
 #ifdef A6_TRACE
   const long long t_cta0 = clock64();
@@ -249,8 +279,8 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       __syncwarp();
     };
     Cursor Lc;   // next tile to LOAD (runs two tiles ahead of the PV cursor)
-    Lc.idx = blockIdx.x; Lc.seq = 0; Lc.j = 0;
-    cursor_skip_empty(Lc, n_items, stride, n_qt, heads, R, kv_len);
+    Lc.pos = pos_first(blockIdx.x, n_qt, heads); Lc.seq = 0; Lc.j = 0;
+    cursor_skip_empty(Lc, walk);
     Cursor Sc = Lc;   // next tile whose QK^T is to be issued
     Cursor Pc = Lc;   // next tile whose PV is to be issued
     // K(g) and V(g) are loaded separately; Q of an item goes with its first tile
@@ -291,28 +321,28 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       __syncwarp();
     };
 
-    if (Lc.idx < n_items) {
+    if (Lc.pos.idx < n_items) {
       // prologue: tiles 0 and 1 in flight, S(0) issued
       load_q(Lc);
       load_k(Lc, 0);
       load_v(Lc, 0);
-      cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
-      if (Lc.idx < n_items) {
+      cursor_next(Lc, walk);
+      if (Lc.pos.idx < n_items) {
         if (Lc.j == 0) load_q(Lc);
         load_k(Lc, 1);
         load_v(Lc, 1);
-        cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
+        cursor_next(Lc, walk);
       }
       issue_s(Sc, 0);
-      cursor_next(Sc, n_items, stride, n_qt, heads, R, kv_len);
+      cursor_next(Sc, walk);
 
-      for (int g = 0; Pc.idx < n_items; ++g) {
+      for (int g = 0; Pc.pos.idx < n_items; ++g) {
         // invariant: Pc = tile g, Sc = tile g+1, Lc = tile g+2
-        if (Sc.idx < n_items) {
+        if (Sc.pos.idx < n_items) {
           issue_s(Sc, g + 1);
-          cursor_next(Sc, n_items, stride, n_qt, heads, R, kv_len);
+          cursor_next(Sc, walk);
           // S(g) has retired (S(g+1) was issued after s_free(g)), so K buffer g&1 can be refilled
-          if (Lc.idx < n_items) load_k(Lc, g + 2);
+          if (Lc.pos.idx < n_items) load_k(Lc, g + 2);
         }
         mbar_wait(&v_full[g & 1], (uint32_t)((g >> 1) & 1));
         mbar_wait(p_full, (uint32_t)(g & 1));        // P(g) in TMEM, O rescaled if it had to be
@@ -331,12 +361,12 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
           }
           __syncwarp();
         }
-        cursor_next(Pc, n_items, stride, n_qt, heads, R, kv_len);
-        if (Lc.idx < n_items) {
+        cursor_next(Pc, walk);
+        if (Lc.pos.idx < n_items) {
           if (Lc.j == 0) load_q(Lc);                 // (after PV(g) was issued: see load_q)
           mbar_wait(pv_done, (uint32_t)(g & 1));     // V buffer g&1 is free once PV(g) retired
           load_v(Lc, g + 2);
-          cursor_next(Lc, n_items, stride, n_qt, heads, R, kv_len);
+          cursor_next(Lc, walk);
         }
       }
     }
@@ -354,11 +384,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     int g = 0;                                       // position in the CTA's tile stream
     int seq = 0;                                     // non-empty items so far
 
-    Item nxt;
-    if ((int)blockIdx.x < n_items) nxt = make_item(blockIdx.x, n_qt, heads, R, kv_len);
-    for (int idx = blockIdx.x; idx < n_items; idx += stride) {
-      const Item it = nxt;
-      if (idx + stride < n_items) nxt = make_item(idx + stride, n_qt, heads, R, kv_len);
+    Pos pos = pos_first(blockIdx.x, n_qt, heads);
+    for (; pos.idx < n_items; pos_advance(pos, step, stride, n_qt, heads)) {
+      const Item it = make_item(pos, R, kv_len);
       if (it.n_tiles == 0) {                         // no valid key at all: zeros
         const int r = threadIdx.x >> 1, h2 = threadIdx.x & 1;   // 256 threads: row x 64-byte half
         const int row = it.q0 + r;
@@ -478,8 +506,8 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       tc_fence_after();
       uint32_t o[32];
       tmem_ld_16x256b_x8(tO_mine, o);
-      const float inv_lo = 1.f / quad_sum(l_lo);
-      const float inv_hi = 1.f / quad_sum(l_hi);
+      const float inv_lo = __fdividef(1.f, quad_sum(l_lo));   // one MUFU.RCP; the result is rounded to bf16
+      const float inv_hi = __fdividef(1.f, quad_sum(l_hi));
       tc_wait_ld();
       tc_fence_before();                             // O is in registers: PV of the next item may overwrite it
       __syncwarp();
@@ -559,8 +587,12 @@ int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, con
   W2V_REQUIRE(B <= A6_MAX_B, "attention: at most %d windows per launch (got %d)", A6_MAX_B, B);
   const long long slots = 2ll * num_sms();           // persistent: two CTAs per SM
   const int grid = (int)(n_items < slots ? n_items : slots);
+  Step step;
+  step.qt = grid % n_qt;
+  step.head = (grid / n_qt) % heads;
+  step.b = (grid / n_qt) / heads;
   ProfScope ps(s, "attention_d64");
-  attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B, kv_len,
+  attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B, step, kv_len,
                                                                 scale_log2, ctx);
   W2V_CHECK_LAUNCH();
   return 0;
