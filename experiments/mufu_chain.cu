@@ -60,6 +60,52 @@ __global__ void k(int iters, const float* in, float scale, long long* cyc, uint3
   sink[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_uint(l);
 }
 
+// mode 0 exp phase in warps 0..7 (2 per sub-partition) while warps 8..15 spin on an mbarrier exactly like
+// ptx.cuh's mbar_wait (try_wait + clock64 watchdog): do waiting warps steal issue slots from the exponentials?
+__device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__global__ void kspin(int iters, const float* in, float scale, long long* cyc, uint32_t* sink, int spin) {
+  __shared__ uint64_t bar;
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(8));
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp >= 8) {
+    if (spin) {
+      long long t0 = clock64();
+      while (!try_wait(b, 0)) { if (clock64() - t0 > 8000000000LL) __trap(); }
+    }
+    return;
+  }
+  float s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = in[i * 32 + (threadIdx.x & 31)];
+  float nm_lo = in[3], nm_hi = in[5];
+  uint32_t acc = 0; float l = 0.f;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float sl0 = 0, sl1 = 0, sh0 = 0, sh1 = 0;
+    uint32_t pk[32];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float e0 = ex2a(fmaf(s[4 * kk + 0], scale, nm_lo)), e1 = ex2a(fmaf(s[4 * kk + 1], scale, nm_lo));
+      const float e2 = ex2a(fmaf(s[4 * kk + 2], scale, nm_hi)), e3 = ex2a(fmaf(s[4 * kk + 3], scale, nm_hi));
+      sl0 += e0; sl1 += e1; sh0 += e2; sh1 += e3;
+      pk[2 * kk] = pack(e0, e1); pk[2 * kk + 1] = pack(e2, e3);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc ^= pk[i];
+    l += sl0 + sl1 + sh0 + sh1;
+    nm_lo += __uint_as_float(acc & 1);
+  }
+  const long long t1 = clock64();
+  if ((threadIdx.x & 31) == 0) { cyc[warp] = t1 - t0; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory"); }
+  sink[threadIdx.x] = acc + __float_as_uint(l);
+}
+
 int main() {
   float* in; long long* cyc; uint32_t* sink;
   cudaMalloc(&in, 64 * 32 * 4); cudaMemset(in, 0, 64 * 32 * 4);
@@ -78,6 +124,12 @@ int main() {
       printf("mode %d warps/CTA %2d (%d per sub-partition): %.0f cycles per 64-exp phase per warp  -> XU busy %.0f %%\n", mode, warps,
              (warps + 3) / 4, (double)mx / iters, 100.0 * ((warps + 3) / 4) * 512.0 / ((double)mx / iters));
     }
+  for (int spin = 0; spin < 2; ++spin) {
+    for (int rep = 0; rep < 2; ++rep) { kspin<<<1, 512>>>(iters, in, 0.125f, cyc, sink, spin); cudaDeviceSynchronize(); }
+    long long h[8]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 8; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("8 exp warps + 8 %s warps: %.0f cycles per 64-exp phase per warp\n", spin ? "mbarrier-spinning" : "exited", (double)mx / iters);
+  }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

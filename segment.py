@@ -5,6 +5,12 @@
     python segment.py ckpt_path=... config_path=... output_dir=... [algorithm=dac|strm|pthr] \
         [infer_data=...] [inference_times=N] [batch_size=14]
 
+Config: conf/segment.yaml (byte-identical to the reference's) composed by Hydra when it is
+importable (`@hydra.main(config_path="conf", config_name="segment")`, reference segment.py:159),
+otherwise by wav2vecsegmenter_b200.config (same defaults list / overrides / interpolation / run dir
+`${output_dir}/${hydra.job.override_dirname}`). Like the reference, `custom_segments.yaml` lands in
+the job's run directory (reference segment.py:175-176 writes relative to Hydra's cwd).
+
 Mechanism (new): each wav is decoded once, all windows of all tilings of a talk go through the
 CUDA SFC forward in device batches (wav2vecsegmenter_b200.pipeline.TalkRunner), the talk vector
 is assembled / NaN-filled / averaged on the GPU, and only the final per-frame probabilities come
@@ -33,10 +39,10 @@ from wav2vecsegmenter_b200.pipeline import TalkRunner  # noqa: E402
 logger = logging.getLogger("segment")
 
 
-def load_model(config, device):
+def load_model(config, device, ckpt_path=None):
     """build SHAS from config.task.model and load the checkpoint (reference segment.py:41-52)"""
-    model = cfglib.instantiate(dict(config.task.model)).to(device)
-    checkpoint = torch.load(config.ckpt_path, map_location="cpu")
+    model = cfglib.instantiate(config.task.model).to(device)
+    checkpoint = torch.load(ckpt_path if ckpt_path is not None else config.ckpt_path, map_location="cpu")
     if config.task.model.finetune_wav2vec:
         model.load_state_dict(checkpoint["state_dict"])
     else:
@@ -46,7 +52,7 @@ def load_model(config, device):
 
 
 def run_algorithm(config, probs, logits=None, vocab=None):
-    algo_conf = dict(config.algorithm)
+    algo_conf = cfglib.to_object(config.algorithm)
     algorithm = algo_conf.pop("tag")
     if algorithm == "dac":
         return pdac(probs, **algo_conf)
@@ -65,7 +71,7 @@ def wav_names(config):
     return [name for name, _ in itertools.groupby(seg_yaml, key=lambda x: x["wav"])]
 
 
-def generate(config, wav_paths=None) -> list:
+def generate(config, wav_paths=None, ckpt_path=None) -> list:
     if torch.cuda.device_count() == 0:
         raise RuntimeError("segment.py (B200 build) needs a CUDA device: there is no CPU path")
     if config.task.get("vocab"):
@@ -81,7 +87,7 @@ def generate(config, wav_paths=None) -> list:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
     device = torch.device("cuda", local)
-    model = load_model(config, device)
+    model = load_model(config, device, ckpt_path)
     runner = TalkRunner(model.engine, batch_size=config.batch_size,
                         segment_sec=config.inference_segment_length,
                         inference_times=config.inference_times, dist_group=group)
@@ -96,7 +102,10 @@ def generate(config, wav_paths=None) -> list:
             yield wave
 
     # pipelined over talks: decode + H2D of the next wav overlap the forward of the current one
+    rank0 = int(os.environ.get("RANK", "0")) == 0
     for wav_path, result in zip(wav_paths, runner.run_stream(waves())):
+        if not rank0:      # every rank holds the gathered probabilities; only rank 0 segments and writes
+            continue
         segments = run_algorithm(config, result.probs)
         yaml_content = update_yaml_content(yaml_content, segments, Path(wav_path).name)
     del model
@@ -104,19 +113,38 @@ def generate(config, wav_paths=None) -> list:
     return yaml_content
 
 
-def main(argv=None):
-    logging.basicConfig(level=logging.INFO)
-    config = cfglib.compose(ROOT / "conf", "segment", list(sys.argv[1:] if argv is None else argv))
-    out_dir = Path(config.output_dir)
-    out_dir.mkdir(parents=True, exist_ok=True)
-    logger.info("Output directory : [%s]", out_dir)
+def _run(config, results_dir: Path) -> None:
+    """reference segment.py:160-177 after config composition"""
+    if config.config_path is not None:
+        prev_cfg = cfglib.load(config.config_path) if isinstance(config, cfglib.Cfg) else None
+        if prev_cfg is None:
+            from omegaconf import OmegaConf  # Hydra path
+
+            config = OmegaConf.merge(OmegaConf.load(config.config_path), config)
+        else:
+            config = cfglib.merge(prev_cfg, config)
+    logger.info("Output directory : [%s]", config.output_dir)
     yaml_content = generate(config)
     logger.info("Number of segments: %d", len(yaml_content))
     if int(os.environ.get("RANK", "0")) == 0:
-        target = out_dir / config.cust_seg_yaml
+        target = results_dir / config.cust_seg_yaml
         with open(target, "w") as f:
             yaml.dump(yaml_content, f, default_flow_style=True)
         logger.info("Saved to [%s].", target)
+
+
+def main(argv=None):
+    logging.basicConfig(level=logging.INFO)
+    try:
+        import hydra  # noqa: F401
+    except ImportError:
+        hydra = None
+    if hydra is not None and argv is None:
+        # Hydra changes into hydra.run.dir before calling the task function (as for the reference)
+        hydra.main(config_path="conf", config_name="segment")(lambda config: _run(config, Path(os.getcwd())))()
+        return
+    config = cfglib.compose(ROOT / "conf", "segment", list(sys.argv[1:] if argv is None else argv))
+    _run(config, cfglib.run_dir(config))
 
 
 if __name__ == "__main__":

@@ -337,7 +337,7 @@ def test_segment_cli_generate(tmp_path):
     (tmp_path / "orig.yaml").write_text(yaml.dump([{"wav": "a.wav", "offset": 0.0, "duration": 1.0}]))
     cfg = cfglib.compose(cli.ROOT / "conf", "segment", [
         f"ckpt_path={tmp_path / 'ckpt.pt'}", f"config_path={tmp_path / 'train.yaml'}", f"output_dir={tmp_path}",
-        "algorithm=pthr", "infer_data=custom", f"infer_data.wav_dir={tmp_path}",
+        "algorithm=pthr", "infer_data=toy", f"infer_data.wav_dir={tmp_path}",
         f"infer_data.orig_seg_yaml={tmp_path / 'orig.yaml'}", "inference_times=2"])
     content = cli.generate(cfg)
     assert len(content) > 0 and set(content[0]) == {"duration", "offset", "rW", "uW", "speaker_id", "wav"}

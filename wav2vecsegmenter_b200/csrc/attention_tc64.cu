@@ -26,6 +26,8 @@
 // Rescaling is lazy (FlashAttention-4): the exponent's running max only advances when a tile max
 // exceeds it by more than 2^8. Replaces Wav2Vec2Attention's softmax(QK^T*scale + key mask) V
 // (HF:500-549).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -36,26 +38,36 @@ namespace {
 constexpr int A6_BM = 128;        // query rows per CTA
 constexpr int A6_BN = 128;        // keys per tile
 constexpr int A6_DH = 64;
-constexpr int A6_THREADS = 288;   // 8 softmax warps + 1 TMA/MMA warp
-constexpr int A6_CTRL_WARP = 8;
+// A CTA holds NG "groups"; a group = 8 softmax warps + 1 TMA/MMA warp working on its own stream of
+// items with its own Q/K/V buffers, barriers and 256 TMEM columns. NG = 1: two CTAs per SM (round 1).
+// NG = 2: ONE CTA per SM whose two groups take turns on the exponentials (see "turn" below).
+constexpr int A6_GROUP_WARPS = 8;                      // softmax warps per group
 constexpr int A6_TILE_BYTES = A6_BN * A6_DH * 2;       // 16 KB: one Q / K / V tile
-constexpr int A6_OFF_Q = 0;                            // 2 buffers (item parity)
+constexpr int A6_OFF_Q = 0;                            // per group: 2 buffers (item parity)
 constexpr int A6_OFF_K = A6_OFF_Q + 2 * A6_TILE_BYTES; // 2 buffers (tile parity)
 constexpr int A6_OFF_V = A6_OFF_K + 2 * A6_TILE_BYTES; // 2 buffers
-constexpr int A6_OFF_BAR = A6_OFF_V + 2 * A6_TILE_BYTES;   // 12 mbarriers + TMEM slot
+constexpr int A6_GROUP_SMEM = A6_OFF_V + 2 * A6_TILE_BYTES;   // 96 KB of tiles per group
+constexpr int A6_GROUP_BARS = 12;                      // mbarriers per group
 // the kernel traps if the dynamic smem base is not 1024-byte aligned (no alignment slack)
-constexpr int A6_OFF_KLEN = A6_OFF_BAR + 128;          // int32 [A6_MAX_B] clamped key lengths
 constexpr int A6_MAX_B = 1024;
-constexpr int A6_SMEM_BYTES = A6_OFF_KLEN + A6_MAX_B * 4;
-constexpr int A6_TMEM_COLS = 256;
+constexpr int a6_off_bar(int ng) { return ng * A6_GROUP_SMEM; }          // ng*12 group barriers, 8 turn barriers
+constexpr int a6_off_misc(int ng) { return a6_off_bar(ng) + 8 * (ng * A6_GROUP_BARS + 8); }   // TMEM slot, done flags
+constexpr int a6_off_klen(int ng) { return a6_off_misc(ng) + 32; }       // int32 [A6_MAX_B] clamped key lengths
+constexpr int a6_smem_bytes(int ng) { return a6_off_klen(ng) + A6_MAX_B * 4; }
+constexpr int a6_threads(int ng) { return ng * (A6_GROUP_WARPS + 1) * 32; }
+constexpr int A6_TMEM_COLS = 256;                      // per group
 constexpr int A6_O_COL = 128;
 constexpr int A6_P_COL = 192;     // P as packed bf16x2: 64 columns = 128 keys (A operand of P V)
 constexpr float A6_RESCALE_THRESHOLD = 8.0f;           // log2 units
 
 __device__ __forceinline__ float ex2a(float x) {
+#ifdef A6_X_NOMUFU
+  return x * 1.0001f;   // timing experiment only (wrong results): no XU instruction in the exponential loop
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -121,7 +133,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 #ifndef A6_TRACE_CTA
 #define A6_TRACE_CTA 5
 #endif
-__device__ long long g_trace[8][8];
+__device__ long long g_trace[8][10];
 __device__ long long g_tile_t[4][64];
 __device__ long long g_ep[8];
 #define A6_E(ev) do { if (blockIdx.x == 5 && threadIdx.x == 0 && seq == 2) g_ep[ev] = clock64() - t_cta0; } while (0)
@@ -206,20 +218,41 @@ __device__ __forceinline__ void cursor_next(Cursor& c, const Walk& w) {
   cursor_skip_empty(c, w);
 }
 
-__global__ void __launch_bounds__(A6_THREADS, 2)
+// Bounded wait on a turn barrier that also gives up (for good) once the partner group has left the
+// kernel: the groups walk streams of different lengths.
+__device__ __forceinline__ bool turn_wait(uint64_t* bar, uint32_t parity, const volatile int* partner_done) {
+  if (mbar_try_wait(bar, parity)) return true;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*partner_done) return false;
+    if (clock64() - t0 > 8000000000LL) {
+      printf("w2vseg: attention turn barrier timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+  return true;
+}
+
+template <int NG>
+__global__ void __launch_bounds__(a6_threads(NG), 3 - NG)
 attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                       int R, int heads, int n_qt, int n_items, int B, Step step, const int* __restrict__ kv_len_g,
-                      float scale_log2, __nv_bfloat16* __restrict__ ctx) {
+                      float scale_log2, __nv_bfloat16* __restrict__ ctx, int use_turn) {
   extern __shared__ uint8_t att_raw[];
   uint8_t* smem = att_raw;
   if ((smem_u32(att_raw) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("w2vseg: attention smem base not 1024-byte aligned\n");
     __trap();
   }
-  uint8_t* sQ = smem + A6_OFF_Q;
-  uint8_t* sK = smem + A6_OFF_K;
-  uint8_t* sV = smem + A6_OFF_V;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR);
+  constexpr int N_SOFT = NG * A6_GROUP_WARPS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_ctrl = warp >= N_SOFT;
+  const int grp = is_ctrl ? warp - N_SOFT : warp / A6_GROUP_WARPS;   // warp-uniform
+  const int lw = warp % A6_GROUP_WARPS;                              // softmax warp within the group
+  uint8_t* sQ = smem + grp * A6_GROUP_SMEM + A6_OFF_Q;
+  uint8_t* sK = smem + grp * A6_GROUP_SMEM + A6_OFF_K;
+  uint8_t* sV = smem + grp * A6_GROUP_SMEM + A6_OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a6_off_bar(NG)) + grp * A6_GROUP_BARS;
   uint64_t* q_full = bars + 0;   // [2]
   uint64_t* k_full = bars + 2;   // [2]
   uint64_t* v_full = bars + 4;   // [2]
@@ -229,19 +262,23 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   uint64_t* pv_done = bars + 9;
   uint64_t* o_free = bars + 10;
   uint64_t* stage_free = bars + 11;   // completion k: the output store of item k has read its staging tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // turn[x][q]: "group x may run its exponentials on SM sub-partition q" (NG = 2 only)
+  uint64_t* turn = reinterpret_cast<uint64_t*>(smem + a6_off_bar(NG)) + NG * A6_GROUP_BARS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a6_off_misc(NG));
+  volatile int* done_flag = reinterpret_cast<volatile int*>(smem + a6_off_misc(NG) + 8);   // [2]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * A6_DH;
-  const int stride = gridDim.x;
-  int* kv_len = reinterpret_cast<int*>(smem + A6_OFF_KLEN);
+  const int stride = gridDim.x * NG;
+  const int vcta = blockIdx.x + grp * gridDim.x;     // this group's slot in the item walk (the longer streams, the first n_items % stride, land on different SMs)
+  int* kv_len = reinterpret_cast<int*>(smem + a6_off_klen(NG));
   const Walk walk = {n_items, stride, n_qt, heads, R, step, kv_len};
-  for (int i = threadIdx.x; i < B; i += A6_THREADS) kv_len[i] = min(__ldg(kv_len_g + i), R);
+  for (int i = threadIdx.x; i < B; i += a6_threads(NG)) kv_len[i] = min(__ldg(kv_len_g + i), R);
+  if (threadIdx.x < 2) done_flag[threadIdx.x] = 0;
 #ifdef A6_TRACE
   const long long t_cta0 = clock64();
 #endif
 
-  if (warp == A6_CTRL_WARP) {
+  if (is_ctrl) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_qkv);
       tma_prefetch_desc(&tmap_out);
@@ -252,20 +289,24 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       mbar_init(pv_done, 1);
       mbar_init(o_free, 8);
       mbar_init(stage_free, 1);
+      if (grp == 0)
+        for (int i = 0; i < 8; ++i) mbar_init(&turn[i], 2);   // the two warps of a group on one sub-partition
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, A6_TMEM_COLS);
-    tmem_relinquish();
+    if (grp == 0) {
+      tmem_alloc(tmem_slot, NG * A6_TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot + (uint32_t)(grp * A6_TMEM_COLS);
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + A6_O_COL;
 
-  if (warp == A6_CTRL_WARP) {
+  if (is_ctrl) {
     // ------------------------------------------------------------ TMA producer + MMA issuer
     // Every lane runs the warp-uniform control flow (descriptors in uniform registers); one elected
     // lane issues the TMA / MMA / commit instructions. The key tiles of all items of this CTA form
@@ -279,7 +320,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       __syncwarp();
     };
     Cursor Lc;   // next tile to LOAD (runs two tiles ahead of the PV cursor)
-    Lc.pos = pos_first(blockIdx.x, n_qt, heads); Lc.seq = 0; Lc.j = 0;
+    Lc.pos = pos_first(vcta, n_qt, heads); Lc.seq = 0; Lc.j = 0;
     cursor_skip_empty(Lc, walk);
     Cursor Sc = Lc;   // next tile whose QK^T is to be issued
     Cursor Pc = Lc;   // next tile whose PV is to be issued
@@ -372,8 +413,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     }
   } else {
     // ------------------------------------------------------------ softmax: warp = 16 rows x 128 keys
-    const int quarter = warp & 3;                    // TMEM lane quarter (hardware: warp id % 4)
-    const int hf = warp >> 2;                        // which 16 rows of the quarter
+    const int quarter = lw & 3;                      // TMEM lane quarter (hardware: warp id % 4) = SM sub-partition
+    const int hf = lw >> 2;                          // which 16 rows of the quarter
+    const int gtid = lw * 32 + lane;                 // thread within the group (0..255)
+    bool partner_gone = (NG == 1) || !use_turn;
     const int row_lo = quarter * 32 + hf * 16 + (lane >> 2);   // this thread's query rows in the tile:
     const int row_hi = row_lo + 8;                              // row_lo and row_lo + 8
     const int cpair = 2 * (lane & 3);                // its columns: 8k + cpair, 8k + cpair + 1
@@ -384,11 +427,11 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     int g = 0;                                       // position in the CTA's tile stream
     int seq = 0;                                     // non-empty items so far
 
-    Pos pos = pos_first(blockIdx.x, n_qt, heads);
+    Pos pos = pos_first(vcta, n_qt, heads);
     for (; pos.idx < n_items; pos_advance(pos, step, stride, n_qt, heads)) {
       const Item it = make_item(pos, R, kv_len);
       if (it.n_tiles == 0) {                         // no valid key at all: zeros
-        const int r = threadIdx.x >> 1, h2 = threadIdx.x & 1;   // 256 threads: row x 64-byte half
+        const int r = gtid >> 1, h2 = gtid & 1;      // 256 threads: row x 64-byte half
         const int row = it.q0 + r;
         __nv_bfloat16* out = ctx + ((long long)(it.row_base + row)) * D + it.head * A6_DH + h2 * 32;
         if (row < R) {
@@ -411,7 +454,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         tc_fence_before();                           // S(g) is in registers: release the S columns
         __syncwarp();                                // for QK^T of tile g+1 right away
         if (lane == 0) mbar_arrive(s_free);
-        if (j == 0 && seq > 0 && threadIdx.x == 0) {   // previous item's output store has left its staging
+        if (j == 0 && seq > 0 && gtid == 0) {        // previous item's output store has left its staging
           bulk_wait_group_read0();                     // tile (= that item's Q buffer): hand it back to
           mbar_arrive(stage_free);                     // the producer (it refills it for item seq+1)
         }
@@ -473,6 +516,13 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         // operand of P V (pk[2k+e]: row lo/hi, packed column 4k + t%4)
         float sl0 = 0.f, sl1 = 0.f, sh0 = 0.f, sh1 = 0.f;
         const float nm_lo = -m_lo, nm_hi = -m_hi;
+        // Turn-taking (NG = 2): the groups alternate on the exponentials, tile by tile and per SM
+        // sub-partition, so that one group's exponential phase (XU + issue slots) overlaps the other
+        // group's latency chain (barrier, TMEM load, row max, P store) instead of both groups doing
+        // either at the same time. Group 0 goes first; turn[x][q] completes once per tile of group 1-x.
+        if (NG == 2 && !partner_gone)
+          partner_gone = !turn_wait(&turn[grp * 4 + quarter], (uint32_t)((g + 1 - grp) & 1), done_flag + (1 - grp));
+        A6_T(7);
         {
           uint32_t pk[32];
 #pragma unroll
@@ -481,10 +531,19 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             const float e1 = ex2a(fmaf(s[4 * k + 1], scale_log2, nm_lo));
             const float e2 = ex2a(fmaf(s[4 * k + 2], scale_log2, nm_hi));
             const float e3 = ex2a(fmaf(s[4 * k + 3], scale_log2, nm_hi));
+#ifndef A6_X_NOSUM
             sl0 += e0; sl1 += e1; sh0 += e2; sh1 += e3;
+#else
+            sl0 = e0; sl1 = e1; sh0 = e2; sh1 = e3;
+#endif
             pk[2 * k + 0] = pack_bf16x2(e0, e1);
             pk[2 * k + 1] = pack_bf16x2(e2, e3);
           }
+          if (NG == 2 && use_turn) {                 // the exponentials have been issued: partner's turn
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&turn[(1 - grp) * 4 + quarter]);
+          }
+          A6_T(8);
           if (!pv_seen) {
             mbar_wait(pv_done, (uint32_t)((g - 1) & 1));
             tc_fence_after();
@@ -527,21 +586,25 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_hi + (uint32_t)((k ^ (row_hi & 7)) << 4)), "r"(v1) : "memory");
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 5, 256;" ::: "memory");
-      if (threadIdx.x == 0) {
+      asm volatile("bar.sync %0, 256;" ::"r"(5 + grp) : "memory");
+      if (gtid == 0) {
         tma_store_3d(&tmap_out, stage, it.head * A6_DH, it.q0, it.b);
         bulk_commit_group();
       }
       ++seq;
     }
-    if (threadIdx.x == 0) bulk_wait_group_read0();   // shared memory must outlive the last store's read
+    if (gtid == 0) bulk_wait_group_read0();          // shared memory must outlive the last store's read
+    if (NG == 2) {                                   // the partner must not wait for a turn that never comes
+      __syncwarp();
+      if (lane == 0) done_flag[grp] = 1;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == A6_CTRL_WARP) {
+  if (is_ctrl && grp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, A6_TMEM_COLS);
+    tmem_dealloc(tmem_base, NG * A6_TMEM_COLS);
   }
 #ifdef A6_TRACE
   if ((blockIdx.x == 5 || blockIdx.x == 100 || blockIdx.x == 153 || blockIdx.x == 290) && threadIdx.x == 0) {
@@ -557,9 +620,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   }
   if (blockIdx.x == A6_TRACE_CTA && threadIdx.x == 0)
     for (int t = 0; t < 8; ++t)
-      printf("tile %d: wait_s %lld ld %lld max %lld pv_wait %lld exp %lld st_wait+arrive %lld | period %lld\n", 20 + t,
+      printf("tile %d: wait_s %lld ld %lld max %lld pv_wait %lld turn %lld exp %lld pst %lld st_wait+arrive %lld | period %lld\n", 20 + t,
              g_trace[t][1] - g_trace[t][0], g_trace[t][2] - g_trace[t][1], g_trace[t][3] - g_trace[t][2],
-             g_trace[t][4] - g_trace[t][3], g_trace[t][5] - g_trace[t][4], g_trace[t][6] - g_trace[t][5],
+             g_trace[t][4] - g_trace[t][3], g_trace[t][7] - g_trace[t][4], g_trace[t][8] - g_trace[t][7], g_trace[t][5] - g_trace[t][8], g_trace[t][6] - g_trace[t][5],
              t ? g_trace[t][0] - g_trace[t - 1][0] : 0ll);
 #endif
 }
@@ -575,25 +638,38 @@ int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, con
   CUtensorMap tm_out;   // [B][R][D]: a box over the end of a window is clipped, not spilled into the next
   W2V_TRY(make_tmap_3d_bf16(&tm_out, ctx, (uint64_t)D, (uint64_t)R, (uint64_t)B, (uint64_t)D, (uint64_t)R * D, 64, A6_BM));
   const float scale_log2 = scale * 1.4426950408889634f;
-  static bool attr = false;
-  if (!attr) {
-    W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        A6_SMEM_BYTES));
-    attr = true;
+  static int use_turn = 1;
+  static int n_groups = 0;   // W2VSEG_ATT64_GROUPS=1: round-1 layout (two independent CTAs per SM), for A/B runs
+  if (n_groups == 0) {
+    const char* e = getenv("W2VSEG_ATT64_GROUPS");
+    const int ng = (e != nullptr && e[0] == '1') ? 1 : 2;
+    W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        a6_smem_bytes(1)));
+    W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        a6_smem_bytes(2)));
+    n_groups = ng;
+    const char* t = getenv("W2VSEG_ATT64_TURN");
+    use_turn = (t != nullptr && t[0] == '0') ? 0 : 1;
   }
   const int n_qt = (R + A6_BM - 1) / A6_BM;
   const long long n_items = (long long)n_qt * heads * B;
   W2V_REQUIRE(n_items < (1ll << 30), "attention: too many work items");
   W2V_REQUIRE(B <= A6_MAX_B, "attention: at most %d windows per launch (got %d)", A6_MAX_B, B);
-  const long long slots = 2ll * num_sms();           // persistent: two CTAs per SM
-  const int grid = (int)(n_items < slots ? n_items : slots);
+  const long long slots = 2ll * num_sms();           // persistent: two item streams per SM
+  const int streams = (int)(n_items < slots ? n_items : slots);
+  const int grid = (streams + n_groups - 1) / n_groups;
+  const int stride = grid * n_groups;
   Step step;
-  step.qt = grid % n_qt;
-  step.head = (grid / n_qt) % heads;
-  step.b = (grid / n_qt) / heads;
+  step.qt = stride % n_qt;
+  step.head = (stride / n_qt) % heads;
+  step.b = (stride / n_qt) / heads;
   ProfScope ps(s, "attention_d64");
-  attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B, step, kv_len,
-                                                                scale_log2, ctx);
+  if (n_groups == 2)
+    attention_tc64_kernel<2><<<grid, a6_threads(2), a6_smem_bytes(2), s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B,
+                                                                          step, kv_len, scale_log2, ctx, use_turn);
+  else
+    attention_tc64_kernel<1><<<grid, a6_threads(1), a6_smem_bytes(1), s>>>(tm, tm_out, R, heads, n_qt, (int)n_items, B,
+                                                                          step, kv_len, scale_log2, ctx, use_turn);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -262,12 +262,14 @@ class SFCEngine:
         return out
 
 
-def moving_average_device(arr, window: int, device="cuda:0"):
+def moving_average_device(arr, window: int, device=None):
     """numpy/torch fp64 vector -> trailing moving average on the GPU, returned as numpy fp64.
     Stand-alone (no model handle needed): lib/segment.py:508-522."""
     import numpy as np
 
     lib = nat.load()
+    if device is None:   # the process's current GPU (under torchrun: LOCAL_RANK's device, not GPU 0)
+        device = torch.device("cuda", torch.cuda.current_device())
     a = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(device)
     out = torch.empty_like(a)
     if a.numel():
