@@ -158,6 +158,18 @@ int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_s
                            float* probs_out, int32_t* included_out, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* w2vseg_sfc_forward writing straight into the row matrix w2vseg_scatter_rows consumes (what
+ * lib/evaluate.py:82-111 keeps per window: probabilities + the `included` flag):
+ *   rows_out[b * row_stride + t]        = probability of frame t (0 where masked), t < R
+ *   rows_out[b * row_stride + R .. row_cols) = 0
+ *   rows_out[b * row_stride + flag_col] = 1.0f / 0.0f: CollateFn's `included` (flag_col < 0: not written)
+ * Requires R <= row_cols <= row_stride and flag_col in [R, row_cols) or negative. */
+int32_t w2vseg_sfc_forward_rows(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                                const int32_t* sample_len, const int32_t* norm_len,
+                                const int32_t* out_len, int32_t B, int64_t l_max, float* rows_out,
+                                int64_t row_stride, int32_t row_cols, int32_t flag_col,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- talk-level reductions (all device pointers) --------------------------------------------- */
 /* talk[0..n_frames) = NaN, then for each window row w: talk[start[w] .. start[w]+count[w]) =
  * (double) rows[w*row_stride .. +count[w]) ; count[w] < 0 writes zeros over -count[w] frames

@@ -132,7 +132,17 @@ def gold_talk(ns, name, spec, seed, n_samples, audio_seed, inference_times, batc
           + ", ".join(f"{t}:{len(out[t + '_bounds'])}" for t in algos))
 
 
-def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_times, batch_size):
+def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_times, batch_size,
+                       fit_batches=None, probs_every=1):
+    """see below; fit_batches: fit the output layer on the features of the first N reference batches
+    only (long talks); probs_every: store every k-th frame of the probability vectors (fp32) instead of
+    all of them (long talks: the fixture pins the yaml / boundaries, the subsample is for diagnosis)."""
+    return _gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_times, batch_size,
+                               fit_batches, probs_every)
+
+
+def _gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_times, batch_size,
+                        fit_batches, probs_every):
     """Boundary-parity fixture with DECISIVE probabilities (what a trained checkpoint produces; the
     random-init tracks of gold_talk hover around the thresholds). Audio = synth.speech_like_audio
     (noise bursts / near-silent pauses); the model is the seeded random one, except that its final
@@ -145,7 +155,8 @@ def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_ti
     m, sd = build_reference_model(ns, spec, seed)
     x, lab = synth.speech_like_audio(n_samples, audio_seed)
     feats = []
-    hook = m.seg_model.layer_norm.register_forward_hook(lambda mod, i, o: feats.append(o.detach().clone()))
+    hook = m.seg_model.layer_norm.register_forward_hook(
+        lambda mod, i, o: feats.append(o.detach().clone()) if fit_batches is None or len(feats) < fit_batches else None)
     out = {}
     with tempfile.TemporaryDirectory() as td:
         wav = Path(td) / "talk.wav"
@@ -162,25 +173,30 @@ def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_ti
         hook.remove()
         n_frames = len(probs0)
         lab = lab[:n_frames]
-        Z = np.zeros((n_frames, spec.hidden))
+        Z = np.zeros((n_frames if fit_batches is None else min(n_frames, fit_batches * batch_size * 1000),
+                      spec.hidden), dtype=np.float32 if fit_batches else np.float64)
         have = np.zeros(n_frames, bool)
         fr = lambda v: int(np.round((v + 1e-6) * 49.95 / 16000))
         j = 0
         for zb in feats:
             for i in range(zb.shape[0]):
                 s0, e0 = fr(ds.starts[j]), fr(ds.ends[j])
-                cnt = min(e0 - s0, zb.shape[1], n_frames - s0)
+                cnt = min(e0 - s0, zb.shape[1], len(Z) - s0)
+                if cnt <= 0:
+                    j += 1
+                    continue
                 Z[s0:s0 + cnt] = zb[i, :cnt].numpy()
                 have[s0:s0 + cnt] = True
                 j += 1
         edge = np.zeros(n_frames, bool)
         for k in np.flatnonzero(np.diff(lab.astype(int)) != 0):
             edge[max(0, k - 3):k + 5] = True
-        sel = have & ~edge
-        A = np.concatenate([Z[sel], np.ones((int(sel.sum()), 1))], 1)
+        sel = (have & ~edge)[:len(Z)]
+        lab_fit = lab[:len(Z)]
+        A = np.concatenate([Z[sel].astype(np.float64), np.ones((int(sel.sum()), 1))], 1)
         G = A.T @ A + 100.0 * np.eye(spec.hidden + 1)
         G[-1, -1] -= 100.0
-        wb = np.linalg.solve(G, A.T @ np.where(lab, 3.5, -3.5)[sel])
+        wb = np.linalg.solve(G, A.T @ np.where(lab_fit, 3.5, -3.5)[sel])
         out_w = torch.tensor(wb[:-1], dtype=torch.float32)[None, :]
         out_b = torch.tensor(wb[-1:], dtype=torch.float32)
         with torch.no_grad():
@@ -191,10 +207,10 @@ def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_ti
         for i in range(inference_times):
             ds.fixed_length_segmentation(i)
             probs, _, _, _ = ns.evaluate.infer(m, loader(), torch.device("cpu"), False, "bce", None)
-            out[f"probs_{i}"] = probs.copy()
+            out[f"probs_{i}"] = probs.copy() if probs_every == 1 else probs[::probs_every].astype(np.float32)
             acc = probs.copy() if acc is None else acc + probs
         acc /= inference_times
-    out["probs_avg"] = acc
+    out["probs_avg"] = acc if probs_every == 1 else acc[::probs_every].astype(np.float32)
     algos = {
         "dac": (ns.segment.pdac, dict(max_segment_length=16, min_segment_length=0.2, threshold=0.5)),
         "strm": (ns.segment.strm, dict(max_segment_length=18, min_segment_length=0.2, min_pause_length=0.2, threshold=0.5)),
@@ -210,8 +226,9 @@ def gold_talk_decisive(ns, name, spec, seed, n_samples, audio_seed, inference_ti
         GOLD / f"{name}.npz",
         spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads]),
         seed=seed, audio_seed=audio_seed, n_samples=n_samples, inference_times=inference_times,
-        batch_size=batch_size, duration_outframes=int(ds.duration_outframes),
-        out_w=out_w.numpy(), out_b=out_b.numpy(), labels=lab, **out)
+        batch_size=batch_size, duration_outframes=int(ds.duration_outframes), probs_every=probs_every,
+        n_frames=len(acc), out_w=out_w.numpy(), out_b=out_b.numpy(),
+        labels=np.packbits(lab) if probs_every > 1 else lab, **out)
     dec = (np.abs(acc - 0.5) > 0.4).mean()
     print(f"{name}: {len(acc)} frames, {dec:.3f} of them with p < 0.1 or p > 0.9, label agreement "
           f"{((acc > 0.5) == lab).mean():.4f}, " + ", ".join(f"{t}:{len(out[t + '_bounds'])}" for t in algos))
@@ -383,6 +400,16 @@ def main():
         # decisive (trained-like) probabilities: the boundary-identity fixtures
         "speech_talk": lambda: gold_talk_decisive(ns, "speech_talk", synth.TINY, 0, 16000 * 400 + 1234, 60, 1, 14),
         "speech_talk_x2": lambda: gold_talk_decisive(ns, "speech_talk_x2", synth.TINY, 0, 16000 * 200 + 777, 61, 2, 3),
+        # the configurations BASELINE.json names, with decisive probabilities: large (24/24) + 24 adapters on a
+        # 104 s talk (one tiling), middle+half (8/16) with two overlapped tilings (configs[3] as written)
+        "speech_talk_large": lambda: gold_talk_decisive(ns, "speech_talk_large", synth.LARGE_ALL, 0,
+                                                        16000 * 104 + 345, 62, 1, 14),
+        "speech_talk_mh_x2": lambda: gold_talk_decisive(ns, "speech_talk_mh_x2", synth.MIDDLE_HALF, 0,
+                                                        16000 * 90 + 1234, 63, 2, 14),
+        # configs[4]: 2 h single stream (360 windows, 359 640 frames): the reference's full yaml for
+        # dac / strm / pthr(+moving average); probabilities stored as an every-8th-frame fp32 sample
+        "speech_talk_2h": lambda: gold_talk_decisive(ns, "speech_talk_2h", synth.TINY, 0, 16000 * 7200, 64, 1, 14,
+                                                     fit_batches=4, probs_every=8),
         # dev-set scoring: two talks with labelled segments, two tilings
         "tiny_eval": lambda: gold_eval(ns, "tiny_eval", synth.TINY, 0, 2, 3),
         "tiny_eval_x1": lambda: gold_eval(ns, "tiny_eval_x1", synth.TINY, 0, 1, 14),

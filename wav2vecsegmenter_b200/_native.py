@@ -64,6 +64,7 @@ SIGNATURES = {
     "w2vseg_encode": (_I32, [_P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "w2vseg_head": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _SZ, _P]),
     "w2vseg_sfc_forward": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "w2vseg_sfc_forward_rows": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _I64, _I32, _I32, _P, _SZ, _P]),
     "w2vseg_scatter_rows": (_I32, [_P, _I64, _P, _P, _I32, _P, _I64, _I32, _P]),
     "w2vseg_nanfill": (_I32, [_P, _I64, _P, _I32, _P]),
     "w2vseg_overlap_average": (_I32, [_P, _I32, _I64, _P, _P]),

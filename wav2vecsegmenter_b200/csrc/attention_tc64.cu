@@ -69,6 +69,24 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 #endif
 }
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], max relative error
+// 1.0e-4 = 1/40 of the bf16 rounding P gets anyway): 8 instructions instead of one MUFU.EX2. The XU pipe runs
+// 16 ex2 per clock per SM (experiments/pipe_rates.cu: 8 cycles per warp instruction per sub-partition), which
+// makes a 128 x 128 x 64 tile cost 1024 XU cycles against 512 tensor cycles; moving a fraction of the
+// exponentials here (FlashAttention-4's trick) shortens the XU-bound phase.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);                        // masked keys (-inf) and underflow: 2^-126 ~ 0
+  const float r = x + 12582912.f;              // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (r - 12582912.f);        // f in [-0.5, 0.5]
+  float p = fmaf(f, 0.05500893f, 0.24221095f);
+  p = fmaf(p, f, 0.6932829f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // p * 2^round(x)
+}
+// which of the 4 elements of every k-group take the polynomial (bit e of the mask for k % 4 == j at bits 4j..4j+3)
+#ifndef A6_POLY_MASK
+#define A6_POLY_MASK 0x0000
+#endif
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -527,10 +545,13 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
           uint32_t pk[32];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float e0 = ex2a(fmaf(s[4 * k + 0], scale_log2, nm_lo));
-            const float e1 = ex2a(fmaf(s[4 * k + 1], scale_log2, nm_lo));
-            const float e2 = ex2a(fmaf(s[4 * k + 2], scale_log2, nm_hi));
-            const float e3 = ex2a(fmaf(s[4 * k + 3], scale_log2, nm_hi));
+            const float x0 = fmaf(s[4 * k + 0], scale_log2, nm_lo), x1 = fmaf(s[4 * k + 1], scale_log2, nm_lo);
+            const float x2 = fmaf(s[4 * k + 2], scale_log2, nm_hi), x3 = fmaf(s[4 * k + 3], scale_log2, nm_hi);
+            const int sel = (A6_POLY_MASK >> (4 * (k & 3))) & 15;
+            const float e0 = (sel & 1) ? ex2_poly(x0) : ex2a(x0);
+            const float e1 = (sel & 2) ? ex2_poly(x1) : ex2a(x1);
+            const float e2 = (sel & 4) ? ex2_poly(x2) : ex2a(x2);
+            const float e3 = (sel & 8) ? ex2_poly(x3) : ex2a(x3);
 #ifndef A6_X_NOSUM
             sl0 += e0; sl1 += e1; sh0 += e2; sh1 += e3;
 #else
@@ -639,10 +660,10 @@ int attention_tc64_launch(const __nv_bfloat16* qkv, int B, int R, int heads, con
   W2V_TRY(make_tmap_3d_bf16(&tm_out, ctx, (uint64_t)D, (uint64_t)R, (uint64_t)B, (uint64_t)D, (uint64_t)R * D, 64, A6_BM));
   const float scale_log2 = scale * 1.4426950408889634f;
   static int use_turn = 1;
-  static int n_groups = 0;   // W2VSEG_ATT64_GROUPS=1: round-1 layout (two independent CTAs per SM), for A/B runs
+  static int n_groups = 0;   // W2VSEG_ATT64_GROUPS=2: one CTA per SM with two groups (A/B runs; measured slower, see profiles/attention_experiments_r02.md)
   if (n_groups == 0) {
     const char* e = getenv("W2VSEG_ATT64_GROUPS");
-    const int ng = (e != nullptr && e[0] == '1') ? 1 : 2;
+    const int ng = (e != nullptr && e[0] == '2') ? 2 : 1;
     W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         a6_smem_bytes(1)));
     W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -394,7 +394,8 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
 
 // ---- head: y (fp32 [B*R, D], updated in place) -> logits / probs --------------------------------
 int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const int32_t* out_len,
-             float* logits, float* probs, cudaStream_t st) {
+             float* logits, float* probs, cudaStream_t st, int64_t prob_stride = 0, int row_cols = 0,
+             int flag_col = -1) {
   const w2vseg_config& c = h->cfg;
   const int D = h->D;
   const int64_t M = (int64_t)B * R;
@@ -431,7 +432,8 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     }
   }
   W2V_TRY(head_final_launch(y, B, R, D, h->head.lnf.g, h->head.lnf.b, c.ln_eps, h->head.wout,
-                            h->head.bout, out_len, logits, probs, st));
+                            h->head.bout, out_len, logits, probs, prob_stride > 0 ? prob_stride : R,
+                            row_cols, flag_col, w.included, st));
   return 0;
 }
 
@@ -624,6 +626,28 @@ int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_s
   W2V_TRY(run_head(h, w, w.h, B, R, out_len, logits_out, probs_out, st));
   if (included_out != nullptr)
     W2V_CHECK_CUDA(cudaMemcpyAsync(included_out, w.included, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int32_t w2vseg_sfc_forward_rows(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                                const int32_t* sample_len, const int32_t* norm_len,
+                                const int32_t* out_len, int32_t B, int64_t l_max, float* rows_out,
+                                int64_t row_stride, int32_t row_cols, int32_t flag_col, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(audio && sample_len && norm_len && out_len && rows_out, "sfc_forward_rows: null argument");
+  W2V_REQUIRE(B > 0 && l_max >= 400 && audio_stride >= l_max,
+              "sfc_forward_rows: bad shape (B=%d, l_max=%lld, stride=%lld)", B, (long long)l_max,
+              (long long)audio_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = w2vseg_frame_stride(l_max);
+  W2V_REQUIRE(row_cols >= R && row_stride >= row_cols && flag_col < row_cols && (flag_col < 0 || flag_col >= R),
+              "sfc_forward_rows: row layout (stride %lld, cols %d, flag col %d) does not hold R=%d frames + flag",
+              (long long)row_stride, row_cols, flag_col, R);
+  Workspace w;
+  W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_TRY(run_head(h, w, w.h, B, R, out_len, nullptr, rows_out, st, row_stride, row_cols, flag_col));
   return 0;
 }
 

@@ -390,7 +390,11 @@ head_final_kernel(const float* __restrict__ y, long long rows, int R,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                   const float* __restrict__ w_out, const float* __restrict__ b_out,
                   const int* __restrict__ out_len, float* __restrict__ logits,
-                  float* __restrict__ probs) {
+                  float* __restrict__ probs, long long prob_stride, int row_cols, int flag_col,
+                  const int* __restrict__ included) {
+  // probs: frame t of window b at probs[b * prob_stride + t]; columns [R, row_cols) of every row are
+  // zeroed and, with flag_col >= 0, column flag_col receives the window's `included` flag as a float
+  // (the row format w2vseg_scatter_rows consumes: no separate copy / fill kernels per batch)
   constexpr int C = 1024;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -426,13 +430,18 @@ head_final_kernel(const float* __restrict__ y, long long rows, int R,
     dot = fmaf(fmaf((v[4 * i + 3] - mean) * rstd, g.w, bt.w), w.w, dot);
   }
   dot = warp_sum(dot);
+  const long long b = row / R;
+  const int t = (int)(row - b * R);
   if (lane == 0) {
-    const long long b = row / R;
-    const int t = (int)(row - b * R);
     const bool keep = t < out_len[b];
     const float logit = dot + b_out[0];
     if (logits != nullptr) logits[row] = keep ? logit : 0.f;
-    if (probs != nullptr) probs[row] = keep ? 1.f / (1.f + expf(-logit)) : 0.f;
+    if (probs != nullptr) probs[b * prob_stride + t] = keep ? 1.f / (1.f + expf(-logit)) : 0.f;
+  }
+  if (t == 0 && probs != nullptr) {
+    for (int c = R + lane; c < row_cols; c += 32)
+      if (c != flag_col) probs[b * prob_stride + c] = 0.f;
+    if (lane == 0 && flag_col >= 0) probs[b * prob_stride + flag_col] = included[b] != 0 ? 1.f : 0.f;
   }
 }
 
@@ -663,13 +672,15 @@ int gather_rows_launch(const float* src, int64_t batch_stride, int B, int T, int
 
 int head_final_launch(const float* y, int B, int R, int C, const float* gamma, const float* beta,
                       float eps, const float* w_out, const float* b_out, const int32_t* out_len,
-                      float* logits, float* probs, cudaStream_t s) {
+                      float* logits, float* probs, int64_t prob_stride, int row_cols, int flag_col,
+                      const int32_t* included, cudaStream_t s) {
   W2V_REQUIRE(C == 1024, "head_final: hidden size %d unsupported (1024 only)", C);
   const long long rows = (long long)B * R;
   if (rows <= 0) return 0;
   ProfScope ps(s, "head_final");
   head_final_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(y, rows, R, gamma, beta, eps, w_out, b_out,
-                                                        out_len, logits, probs);
+                                                        out_len, logits, probs, prob_stride, row_cols,
+                                                        flag_col, included);
   W2V_CHECK_LAUNCH();
   return 0;
 }

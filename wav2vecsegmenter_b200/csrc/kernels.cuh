@@ -46,7 +46,8 @@ int gather_rows_launch(const float* src, int64_t batch_stride, int B, int T, int
 // lib/evaluate.py:82-91). logits/probs [B*R] (either may be null).
 int head_final_launch(const float* y, int B, int R, int C, const float* gamma, const float* beta,
                       float eps, const float* w_out, const float* b_out, const int32_t* out_len,
-                      float* logits, float* probs, cudaStream_t s);
+                      float* logits, float* probs, int64_t prob_stride, int row_cols, int flag_col,
+                      const int32_t* included, cudaStream_t s);
 
 // fused non-causal attention, key-length masked (HF:500-549; torch MHA in lib/models.py:291-300)
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,

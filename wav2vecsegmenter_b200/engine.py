@@ -225,6 +225,28 @@ class SFCEngine:
         )
         return logits_out, probs_out
 
+    def sfc_forward_rows(self, audio: torch.Tensor, sample_len, norm_len, out_len, l_max: int,
+                         rows_out: torch.Tensor, flag_col: int = -1):
+        """fused encode + head writing probabilities (and the `included` flag in column flag_col)
+        straight into `rows_out` fp32 [B, cols] (row stride = rows_out.stride(0)): the row matrix
+        scatter_rows consumes. Columns beyond the batch's frame stride are zeroed."""
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.dim() == 2 and audio.stride(1) == 1
+        assert rows_out.is_cuda and rows_out.dtype == torch.float32 and rows_out.dim() == 2 and rows_out.stride(1) == 1
+        B = audio.shape[0]
+        assert rows_out.shape[0] == B
+        sl = self._i32(sample_len, self.device)
+        nl = self._i32(norm_len, self.device)
+        ol = self._i32(out_len, self.device)
+        ws = self._workspace(B, l_max)
+        nat.check(
+            self.lib.w2vseg_sfc_forward_rows(self._h, audio.data_ptr(), audio.stride(0), sl.data_ptr(),
+                                             nl.data_ptr(), ol.data_ptr(), B, int(l_max), rows_out.data_ptr(),
+                                             rows_out.stride(0), rows_out.shape[1], int(flag_col),
+                                             ws.data_ptr(), ws.numel(), self._stream()),
+            "w2vseg_sfc_forward_rows",
+        )
+        return rows_out
+
     # ------------------------------------------------------------------ talk-level reductions
     def scatter_rows(self, rows: torch.Tensor, start, count, n_frames: int, flag_col: int = -1) -> torch.Tensor:
         """rows fp32 [W, stride] -> talk vector fp64 [n_frames] (NaN where no window wrote);

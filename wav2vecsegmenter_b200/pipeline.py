@@ -277,7 +277,6 @@ class TalkRunner:
 
         eng = self.engine
         rows = torch.empty(len(wins), r_max + 1, dtype=torch.float32, device=eng.device)
-        flags = torch.empty(len(wins), dtype=torch.int32, device=eng.device)
         main = torch.cuda.current_stream(eng.device)
 
         def need(group):   # per talk: one past the last sample the device batch reads
@@ -299,7 +298,7 @@ class TalkRunner:
             lmax = max(w.n_samples for w in group)
             if lmax < 400:
                 rows[b0: b0 + len(group)].zero_()
-                flags[b0: b0 + len(group)] = 1
+                rows[b0: b0 + len(group), r_max] = 1.0
                 continue  # shorter than one receptive field: no frames at all
             first = group[0]
             step = group[1].start - first.start if len(group) > 1 else lmax
@@ -319,17 +318,11 @@ class TalkRunner:
             else:
                 meta = torch.tensor([[w.n_samples for w in group], [w.norm_len for w in group],
                                      [w.out_len for w in group]], dtype=torch.int32).to(eng.device, non_blocking=True)
-            R = eng.frame_stride(lmax)
-            _, probs = eng.sfc_forward(stage, meta[0], meta[1], meta[2], lmax,
-                                       logits_out=self._logits_scratch(len(group), R),
-                                       included_out=flags[b0: b0 + len(group)])
-            rows[b0: b0 + len(group), :R] = probs
-            if R < r_max:
-                rows[b0: b0 + len(group), R:r_max].zero_()
+            # probabilities, zero tail and the `included` flag land in `rows` straight from the head kernel
+            eng.sfc_forward_rows(stage, meta[0], meta[1], meta[2], lmax, rows[b0: b0 + len(group)], flag_col=r_max)
             if gi + 1 < len(groups):   # the next batch's samples travel while this one computes
                 for t, upto in need(groups[gi + 1]).items():
                     waves_dev[t].upload_to(upto)
-        rows[:, r_max] = flags.to(torch.float32)
         return rows
 
     def _side(self):
@@ -339,15 +332,6 @@ class TalkRunner:
         if side is None:
             side = self._side_stream = torch.cuda.Stream(self.engine.device)
         return side
-
-    def _logits_scratch(self, b: int, r: int):
-        import torch
-
-        buf = getattr(self, "_logits_buf", None)
-        if buf is None or buf.shape[0] < b or buf.shape[1] != r:
-            buf = torch.empty(b, r, dtype=torch.float32, device=self.engine.device)
-            self._logits_buf = buf
-        return buf[:b]
 
     def run(self, waves: list[np.ndarray]) -> list[TalkResult]:
         """waves: one float32 array of raw samples per talk. Returns per-talk probabilities."""
