@@ -51,12 +51,22 @@ def work_model(keep=24, adapters=24, D=1024, F=4096, A=512, HF=2048, T=T_FRAMES)
     return sum(fl.values()), fl
 
 
+def workload_config(world: int) -> dict:
+    """the `config` object of the JSON line: identical for the native and the reference arm"""
+    return {"workload": "large (24/24) + 24 FFN adapters SFC inference, batch 14 x 20 s windows per GPU per step",
+            "global_batch_windows": world * BATCH, "window_samples": WIN_SAMPLES,
+            "frames_per_window": T_FRAMES,
+            "parallelism": f"dp{world} (windows sharded, NCCL all_gather of probability rows)" if world > 1 else "single GPU",
+            "l2": "inputs rotate over 4 batches; per-step working set ~2.1 GB >> 126 MB L2",
+            "weights": "random-init, seed 0"}
+
+
 def read_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
         return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
-                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+                "hbm_gbs": d.get("hbm_gbs"), "sm_max_mhz": d.get("sm_max_mhz"), "source": "measured (MEASURED_PEAKS.json)"}
     return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
             "source": "fallback (B200_PROFILING.md)"}
 
@@ -258,6 +268,50 @@ def run_native(args):
     e2e_value = audio_sec / (float(t.item()) / 1e3)
     e2e_d2h = int(last.probs.nbytes + sum(x.nbytes for x in last.per_tiling))
 
+    # ---- BASELINE.json configs[2]: STRONG scaling. A fixed job — 10 h of synthetic talk-length audio
+    # (40 talks x 900 s, 1 800 windows), pinned host samples in, per-frame probabilities of every talk on
+    # rank 0's host out — through TalkRunner.run(): windows sharded over the ranks, ONE NCCL all_gather of
+    # the probability rows, rank 0 assembles the talks. Wall clock, max over ranks. The ideal for N ranks is
+    # measured in the same run: every rank processes 1/N of the job on its own (no exchange, no assembly of
+    # the other ranks' talks); efficiency = that time / the sharded job's time.
+    config3 = None
+    if not args.no_strong:
+        hours = float(os.environ.get("W2VSEG_BENCH_STRONG_HOURS", "10"))
+        n_talks = 40
+        talk_n = int(round(hours * 3600 / n_talks * 16000))
+        distinct = [(torch.randn(talk_n, generator=torch.Generator().manual_seed(31 + i)) * 0.1).pin_memory().numpy()
+                    for i in range(4)]
+        job = [distinct[i % 4] for i in range(n_talks)]
+        grp = dist.group.WORLD if world > 1 else None
+        sharded = TalkRunner(eng, batch_size=BATCH, segment_sec=WIN_SEC, inference_times=1, dist_group=grp)
+        alone = TalkRunner(eng, batch_size=BATCH, segment_sec=WIN_SEC, inference_times=1)
+
+        def wall(fn):
+            barrier()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), out
+
+        sharded.run(job[: max(2, world)], results_on=0)                      # warm-up: allocations, NCCL channels
+        t_job, res = min((wall(lambda: sharded.run(job, results_on=0)) for _ in range(2)), key=lambda x: x[0])
+        share = job[: n_talks // world] if n_talks % world == 0 else job[: n_talks // world + 1]
+        t_share = t_job
+        if world > 1:
+            alone.run(share[:1])
+            t_share, _ = min((wall(lambda: alone.run(share)) for _ in range(2)), key=lambda x: x[0])
+        audio_s = n_talks * talk_n / 16000
+        config3 = {"workload": f"{hours:g} h of synthetic talks ({n_talks} x {talk_n / 16000:.0f} s, "
+                               f"{n_talks * ((talk_n + WIN_SAMPLES - 1) // WIN_SAMPLES)} windows), strong scaling over {world} GPU(s)",
+                   "audio_s_per_s": round(audio_s / t_job, 1), "wall_s": round(t_job, 4),
+                   "ideal_wall_s": round(t_share, 4), "efficiency_vs_n1": round(t_share / t_job, 4),
+                   "efficiency_definition": "wall time of ONE rank processing 1/N of the job alone (no exchange) / wall time of the sharded job, same run",
+                   "frames_out": int(sum(len(r.probs) for r in res)) if res is not None else None,
+                   "api": "wav2vecsegmenter_b200.pipeline.TalkRunner.run(waves, results_on=0)"}
+
     # ---- per-kernel device timing (CUDA events around every launch, on the launching stream)
     roofline, kernels = None, None
     cpu_baseline = None
@@ -279,25 +333,55 @@ def run_native(args):
         gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_names)
         gemm_fl = sum(fl[k] for k in gemm_names) * BATCH
         step_ms = sum(k["ms_per_step"] for k in kernels.values())
-        dom = "gemm.ffn_up"   # the launch family with the largest share of the step
-        dom_ms, dom_n = kernels[dom]["ms_per_step"], kernels[dom]["launches_per_step"]
-        achieved = fl[dom] * BATCH / (dom_ms / 1e3) / 1e12
+        # Launch families grouped by the kernel FUNCTION that runs them; the roofline block reports the function
+        # with the largest measured share of the step, and lists every tensor-bound family (incl. attention,
+        # whose second bound is the XU pipe: 16 ex2 / clk / SM) with its own fraction so that the most
+        # flattering family cannot hide the others.
+        functions = {
+            "gemm_tc2_kernel": gemm_names,
+            "attention_tc64_kernel": [k for k in kernels if k == "attention_d64"],
+            "attention_tc_kernel<128>": [k for k in kernels if k == "attention_d128"],
+            "posconv_tc_kernel": [k for k in kernels if k == "gemm.pos_conv"],
+            "layernorm kernels": [k for k in kernels if k in ("layernorm", "ln_gelu.conv")],
+            "conv0_tc_kernel": [k for k in kernels if k == "conv0_ln_gelu"],
+        }
+        fn_ms = {f: sum(kernels[k]["ms_per_step"] for k in ks) for f, ks in functions.items() if ks}
+        dom_fn = max(fn_ms, key=fn_ms.get)
+        sm_hz = (clocks or {}).get("sm_mhz") or (peaks.get("sm_max_mhz") or 1965.0)
+        families = {}
+        for k in sorted((k for k in kernels if k in fl and kernels[k]["ms_per_step"] > 0 and k != "head_final"),
+                        key=lambda k: -kernels[k]["ms_per_step"]):
+            tf = fl[k] * BATCH / (kernels[k]["ms_per_step"] / 1e3) / 1e12
+            families[k] = {"ms_per_step": round(kernels[k]["ms_per_step"], 4), "tflops": round(tf, 1),
+                           "frac": round(tf / peaks["tflops_sustained"], 4),
+                           "share_of_step": round(kernels[k]["ms_per_step"] / step_ms, 4)}
+        if "attention_d64" in families:
+            # exponentials per step / (16 per clock per SM x 148 SMs x the SM clock sampled during the timed region)
+            n_exp = 24 * BATCH * 16 * T_FRAMES * T_FRAMES
+            xu_peak = 16 * 148 * sm_hz * 1e6
+            families["attention_d64"]["xu_frac"] = round(n_exp / (kernels["attention_d64"]["ms_per_step"] / 1e3) / xu_peak, 4)
+            families["attention_d64"]["xu_note"] = f"MUFU.EX2 issue rate at the sampled {sm_hz:.0f} MHz; a 128x128x64 tile costs 1024 XU vs 512 tensor cycles"
+        dom_ks = functions[dom_fn]
+        dom_ms = fn_ms[dom_fn]
+        dom_n = sum(kernels[k]["launches_per_step"] for k in dom_ks)
+        dom_fl = sum(fl[k] for k in dom_ks) * BATCH
+        achieved = dom_fl / (dom_ms / 1e3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "gemm_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("kernels", {}).get(dom, {}).get("dram_bytes_per_launch")
+        if tp.exists() and dom_fn == "gemm_tc2_kernel":
+            traffic = json.loads(tp.read_text()).get("kernels", {}).get("gemm.ffn_up", {}).get("dram_bytes_per_launch")
         roofline = {
-            "kernel": "gemm_tc2_kernel<bf16-out> FFN-up launches (M=13986 N=4608 K=1024, bias+GELU/ReLU; tcgen05 cta_group::2 / TMEM / TMA)",
+            "kernel": f"{dom_fn} (all {int(dom_n)} launches per step: " + ", ".join(sorted(dom_ks)) + "; tcgen05 cta_group::2 / TMEM / TMA)",
+            "selection": "kernel function with the largest measured time per step (CUDA events around every launch)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
             "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
             "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
-            "traffic": traffic,
+            "traffic": traffic, "traffic_note": "dram bytes of ONE FFN-up launch (ncu --set full, profiles/gemm_traffic.json); algorithmic 167 MB",
             "launches_per_step": dom_n, "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
-            "algorithmic_gflop_per_launch": round(fl[dom] * BATCH / dom_n / 1e9, 1),
+            "algorithmic_gflop_per_launch": round(dom_fl / dom_n / 1e9, 1),
             "share_of_step": round(dom_ms / step_ms, 4),
-            "all_gemm256": {"tflops": round(gemm_fl / (gemm_ms / 1e3) / 1e12, 1),
-                            "frac": round(gemm_fl / (gemm_ms / 1e3) / 1e12 / peaks["tflops_sustained"], 4),
-                            "share_of_step": round(gemm_ms / step_ms, 4)},
+            "families": families,
+            "function_ms_per_step": {f: round(v, 4) for f, v in sorted(fn_ms.items(), key=lambda kv: -kv[1])},
             "whole_path_frac": round(value / world * (total_fl / WIN_SEC) / 1e12 / peaks["tflops_sustained"], 4),
         }
         # memory-bound kernels: ALGORITHMIC bytes per step (each tensor read / written once)
@@ -327,11 +411,7 @@ def run_native(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "large (24/24) + 24 FFN adapters SFC inference, batch 14 x 20 s windows per GPU per step",
-                       "global_batch_windows": world * BATCH, "window_samples": WIN_SAMPLES,
-                       "frames_per_window": T_FRAMES, "parallelism": f"dp{world} (windows sharded, NCCL all_gather of probability rows)" if world > 1 else "single GPU",
-                       "l2": "inputs rotate over 4 batches; per-step working set ~2.1 GB >> 126 MB L2",
-                       "weights": "random-init, seed 0"},
+            "config": workload_config(world),
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s",
                     "h2d_bytes_per_step": BATCH * WIN_SAMPLES * 4, "d2h_bytes_per_step": e2e_d2h,
                     "api": "wav2vecsegmenter_b200.pipeline.TalkRunner.run_stream (host waves in, per-frame probabilities out; H2D of talk k+1 and D2H of talk k-1 overlap the forward of talk k)"},
@@ -339,6 +419,7 @@ def run_native(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "config3": config3,
             "kernels": kernels,
         }
         print(json.dumps(line), flush=True)
@@ -393,32 +474,36 @@ def run_reference(args):
     spec = synth.LARGE_ALL
     sd = synth.random_state_dict(spec, seed=0)
     g = torch.Generator().manual_seed(99)
-    n_win = 2  # bounded sample: 2 of the 14 windows of a batch per step (~15 s for 8 steps on 16 cores)
+    n_win = BATCH   # one step = the full 14-window batch of the native arm (same config)
     audio = sfc_oracle.normalize_rows(torch.randn(n_win, WIN_SAMPLES, generator=g), [True] * n_win)
     out_mask = torch.ones(n_win, T_FRAMES, dtype=torch.bool)
-    steps = min(args.steps, 8)
-    warm = min(args.warmup, 1)
+    budget_s = float(os.environ.get("W2VSEG_REF_BUDGET_S", "150"))   # keeps the whole run within a few minutes
 
     def step():
         with torch.no_grad():
             sfc_oracle.batch_probs(sd, audio, [WIN_SAMPLES] * n_win, out_mask, spec.keep_layers, spec.head_heads)
 
-    for _ in range(warm):
+    warm = 0
+    t_w = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
         step()
+        warm += 1
+    per_step = (time.perf_counter() - t_w) / max(warm, 1) if warm else 15.0
+    steps = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
+    while steps < args.steps and (steps == 0 or (time.perf_counter() - t0) + per_step <= budget_s):
         step()
+        steps += 1
     dt = time.perf_counter() - t0
     value = n_win * WIN_SEC * steps / dt
-    sample = (f"each step = {n_win} x 20 s window (bounded sample of the 14-window batch), fp32 torch CPU, "
-              f"{cores} threads; {steps} timed steps (capped from --steps {args.steps})")
+    sample = (f"each step = the full batch of {n_win} x 20 s windows, fp32 torch CPU kernels (what the reference runs), "
+              f"{cores} threads; {steps} timed step(s) of --steps {args.steps} (wall budget {budget_s:.0f} s), {warm} warm-up")
     line = {
         "impl": "reference", "metric": "SFC audio-sec/sec (large 24/24)", "value": round(value, 2),
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": round(dt / steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "large (24/24) + 24 FFN adapters SFC inference, batch 14 x 20 s windows per GPU per step",
-                   "weights": "random-init, seed 0"},
+        "config": workload_config(max(1, int(os.environ.get("WORLD_SIZE", "1")))),
         "cpu_baseline": {"value": round(value, 2), "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -432,6 +517,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 10 h strong-scaling leg (config3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -114,6 +114,25 @@ int32_t w2vseg_set_weight(w2vseg_handle* h, const char* name, const float* src_d
 /* Must be called after all weights are set (checks completeness, runs the folding kernels). */
 int32_t w2vseg_finalize_weights(w2vseg_handle* h, void* stream);
 
+/* ---- bias correction for the bf16 weight rounding (optional, after finalize) -------------------
+ * The matrices are stored in bf16; y = W x + b then carries the error (bf16(W) - W) x, whose mean over
+ * frames is NOT zero: activations have a large frame-independent component, so every layer adds a constant
+ * vector and the logits of a 24-layer model end up shifted by a frame-independent offset (+0.033 for the
+ * random-init large model, profiles/parity_r02.md). Standard post-training-quantisation bias correction
+ * removes it: b' = b - (bf16(W) - W) E[x], with E[x] measured on a calibration signal.
+ *   1. w2vseg_calibrate: one forward over `audio` (any speech-like signal; same arguments as
+ *      w2vseg_sfc_forward) that records the mean input row of every GEMM in the handle. The positional
+ *      conv, whose fp32 weight-norm factors the handle keeps, is corrected here.
+ *   2. w2vseg_correct_bias(name, src): once per matrix tensor, with the SAME fp32 tensor that was given to
+ *      w2vseg_set_weight (names without a bf16 matrix are accepted and ignored).
+ * w2vseg_finalize_weights resets every bias to its checkpoint value; correcting a matrix twice without a
+ * finalize in between is an error (W2VSEG_ERR_STATE). */
+int32_t w2vseg_calibrate(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                         const int32_t* sample_len, const int32_t* norm_len, const int32_t* out_len,
+                         int32_t B, int64_t l_max, void* workspace, size_t workspace_bytes, void* stream);
+int32_t w2vseg_correct_bias(w2vseg_handle* h, const char* name, const float* src_device, int64_t numel,
+                            void* stream);
+
 /* ---- SFC forward ---------------------------------------------------------------------------- */
 /* scratch bytes needed by encode / head / sfc_forward for B windows of at most l_max samples */
 size_t w2vseg_workspace_bytes(const w2vseg_handle* h, int32_t B, int64_t l_max);

@@ -401,11 +401,11 @@ def main():
         "speech_talk": lambda: gold_talk_decisive(ns, "speech_talk", synth.TINY, 0, 16000 * 400 + 1234, 60, 1, 14),
         "speech_talk_x2": lambda: gold_talk_decisive(ns, "speech_talk_x2", synth.TINY, 0, 16000 * 200 + 777, 61, 2, 3),
         # the configurations BASELINE.json names, with decisive probabilities: large (24/24) + 24 adapters on a
-        # 104 s talk (one tiling), middle+half (8/16) with two overlapped tilings (configs[3] as written)
+        # 420 s talk (one tiling), middle+half (8/16) with two overlapped tilings (configs[3] as written)
         "speech_talk_large": lambda: gold_talk_decisive(ns, "speech_talk_large", synth.LARGE_ALL, 0,
-                                                        16000 * 104 + 345, 62, 1, 14),
+                                                        16000 * 420 + 345, 62, 1, 14),
         "speech_talk_mh_x2": lambda: gold_talk_decisive(ns, "speech_talk_mh_x2", synth.MIDDLE_HALF, 0,
-                                                        16000 * 90 + 1234, 63, 2, 14),
+                                                        16000 * 300 + 1234, 63, 2, 14),
         # configs[4]: 2 h single stream (360 windows, 359 640 frames): the reference's full yaml for
         # dac / strm / pthr(+moving average); probabilities stored as an every-8th-frame fp32 sample
         "speech_talk_2h": lambda: gold_talk_decisive(ns, "speech_talk_2h", synth.TINY, 0, 16000 * 7200, 64, 1, 14,

@@ -51,10 +51,13 @@ sharded = TalkRunner(eng, batch_size=14, inference_times=2, dist_group=dist.grou
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 same = all(np.array_equal(a.probs, b.probs) for a, b in zip(single, sharded))
+# results_on=0: only rank 0 assembles the talks (what segment.py uses); the other ranks get None
+r0 = TalkRunner(eng, batch_size=14, inference_times=2, dist_group=dist.group.WORLD if world > 1 else None).run(waves, results_on=0)
+same_r0 = (r0 is None) if rank != 0 else all(np.array_equal(a.probs, b.probs) for a, b in zip(single, r0))
 if rank == 0:
     print(json.dumps({"world": world, "talks": args.talks, "audio_seconds": float(sum(len(w) for w in waves) / 16000),
-                      "frames": int(sum(len(r.probs) for r in single)), "bit_identical_to_single_gpu": bool(same),
+                      "frames": int(sum(len(r.probs) for r in single)), "bit_identical_to_single_gpu": bool(same), "rank0_only_results_identical": bool(same_r0),
                       "sharded_wall_s": round(dt, 3)}))
-assert same
+assert same and same_r0
 if world > 1:
     dist.destroy_process_group()

@@ -12,7 +12,11 @@ from util import load_gold, make_batch, spec_of  # noqa: E402
 from wav2vecsegmenter_b200 import synth  # noqa: E402
 from wav2vecsegmenter_b200.engine import SFCEngine  # noqa: E402
 
-for name in ["tiny_batch", "middle_window", "middle_half_batch", "large_batch"]:
+import os
+
+for name, corr in [(n, c) for n in ["tiny_batch", "middle_window", "middle_half_batch", "large_batch"] for c in ("0", "1")]:
+    os.environ["W2VSEG_BIAS_CORRECTION"] = corr
+    print(f"--- {name}, bias correction {'on' if corr == '1' else 'off'}")
     g = load_gold(name)
     spec = spec_of(g)
     lens = [int(x) for x in g["lens"]]

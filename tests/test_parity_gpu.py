@@ -54,9 +54,16 @@ def test_probs_match_reference_golden(name):
     assert (p[~g["out_mask"]] == 0).all() and (l[~g["out_mask"]] == 0).all()
     # frames the mask excludes beyond T stay zero too
     assert (probs[:, T:].cpu().numpy() == 0).all()
-    # decisions at the 0.5 threshold (pDAC/pSTRM): at least 99 % identical
-    agree = ((p > 0.5) == (g["probs"] > 0.5))[g["out_mask"]].mean()
-    assert agree >= 0.97, f"{name}: only {agree:.4f} of frames on the same side of 0.5"
+    # decisions at the 0.5 threshold (pDAC/pSTRM): every frame whose margin in the reference exceeds the
+    # tolerance must fall on the same side; overall >= 99 % (random-init probabilities hover around 0.5:
+    # measured 99.5 % for large_batch, 99.9-100 % for the others, profiles/parity_r02.md)
+    same = (p > 0.5) == (g["probs"] > 0.5)
+    decisive = np.abs(g["probs"] - 0.5) > PROB_TOL
+    assert same[decisive & g["out_mask"]].all()
+    agree = same[g["out_mask"]].mean()
+    assert agree >= 0.99, f"{name}: only {agree:.4f} of frames on the same side of 0.5"
+    if name == "large_batch":   # the headline model: bias-corrected bf16 weights leave half the tolerance as margin
+        assert err <= 1e-2, f"{name}: max-abs prob err {err}"
 
 
 @pytest.mark.parametrize("name", ["tiny_batch", "middle_half_batch"])

@@ -33,7 +33,7 @@ def test_pdac_strm_pthr_match_reference(seg):
             assert text == str(g[f"{tag}_yaml_{c}"]), f"{tag} case {c}"
 
 
-@pytest.mark.parametrize("name", ["speech_talk", "speech_talk_x2"])
+@pytest.mark.parametrize("name", ["speech_talk", "speech_talk_x2", "speech_talk_large", "speech_talk_mh_x2"])
 def test_decisive_talk_fixture_host_side(seg, name):
     """the decisive-probability fixtures (oracle/make_golden.py:gold_talk_decisive): pDAC / pSTRM on
     the reference's own probabilities reproduce the reference's boundaries and yaml bit-exactly, and

@@ -86,15 +86,15 @@ def test_talk_probs_and_segments(name, tiny_engine, seg):
     # ... and on the CUDA path's own probabilities. With RANDOM-INIT weights the probabilities
     # are a noisy track hovering around the thresholds (not the saturated 0/1 output of a trained
     # model), so a handful of frames within the bf16 error of the threshold flip and can move a
-    # boundary of the 4-9 segments here; the agreement is printed (-> profiles/parity_r01.md) and
-    # only loosely bounded. What IS guaranteed: every threshold decision whose margin in the
-    # reference exceeds the probability tolerance is reproduced.
+    # boundary of the 4-9 segments here; the agreement is only printed (-> profiles/parity_r02.md).
+    # What IS asserted: every threshold decision whose margin in the reference exceeds the
+    # probability tolerance is reproduced. Boundary identity (>= 99 %) is asserted on the
+    # decisive-probability fixtures below, for every model configuration BASELINE.json names.
     for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
         segs = fn(res.probs, **ALGOS[tag])
         got = np.array([[s.start, s.end] for s in segs]).reshape(-1, 2)
         agree = boundary_agreement(got, g[f"{tag}_bounds"])
         print(f"PARITY {name} {tag}: {len(segs)} segments vs {len(g[tag + '_bounds'])}, boundary agreement {agree:.3f}")
-        assert agree >= 0.4, (tag, agree)
     ref_p = g["probs_avg"]
     for thr in (0.5, 0.1):
         decisive = np.abs(ref_p - thr) > PROB_TOL
@@ -158,6 +158,96 @@ def test_boundaries_identical_on_decisive_probabilities(seg):
     print(f"PARITY decisive talks: pDAC+pSTRM {n_same}/{n_ref} boundaries identical ({n_same / n_ref:.4f}), "
           f"{n_near / n_ref:.4f} within one frame")
     assert n_same / n_ref >= 0.99
+
+
+def _decisive_engine(g):
+    from wav2vecsegmenter_b200.engine import SFCEngine
+
+    spec = spec_of(g)
+    sd = synth.random_state_dict(spec, int(g["seed"]))
+    sd["seg_model.output_layer.weight"] = torch.from_numpy(g["out_w"].copy())
+    sd["seg_model.output_layer.bias"] = torch.from_numpy(g["out_b"].copy())
+    eng = SFCEngine(spec)
+    eng.load_state_dict(sd)
+    return eng
+
+
+@pytest.mark.parametrize("name", ["speech_talk_large", "speech_talk_mh_x2"])
+def test_boundaries_identical_headline_configs(name, seg):
+    """The same boundary-identity claim on the model configurations BASELINE.json names: large (24/24) +
+    24 adapters over a 420 s talk (one tiling, configs[1]/[2]) and middle+half (8/16) with two overlapped
+    tilings over 300 s (configs[3] as written). Golden boundaries / probabilities: the unmodified reference
+    pipeline in fp32 on CPU with the calibrated output layer stored in the fixture
+    (oracle/make_golden.py:gold_talk_decisive). >= 99 % of pDAC + pSTRM boundaries identical, per fixture."""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    g = load_gold(name)
+    eng = _decisive_engine(g)
+    it = int(g["inference_times"])
+    wave_f = speech_wave(int(g["n_samples"]), int(g["audio_seed"]))
+    res = TalkRunner(eng, batch_size=int(g["batch_size"]), segment_sec=20, inference_times=it).run([wave_f])[0]
+    ref_p = g["probs_avg"]
+    assert len(res.probs) == len(ref_p) == int(g["duration_outframes"])
+    err = np.abs(res.probs - ref_p)
+    assert err.max() <= PROB_TOL, err.max()
+    t_ref = t_same = 0
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+        segs = fn(res.probs, **ALGOS[tag])
+        got = np.array([[s.start, s.end] for s in segs]).reshape(-1, 2)
+        ref = g[f"{tag}_bounds"]
+        exact = boundary_agreement(got, ref, tol=0.0)
+        text = yaml.dump(seg.update_yaml_content([], segs, "talk.wav"), default_flow_style=True)
+        print(f"PARITY {name} {tag}: {len(segs)} segments vs {len(ref)}; boundaries identical {exact:.4f}; "
+              f"yaml byte-identical: {text == str(g[tag + '_yaml'])}")
+        assert len(segs) == len(ref), tag
+        if tag != "pthr":
+            t_ref += ref.size
+            t_same += int(round(exact * ref.size))
+    print(f"PARITY {name}: pDAC+pSTRM {t_same}/{t_ref} boundaries identical ({t_same / t_ref:.4f}); "
+          f"max-abs prob err {err.max():.4f}, mean {err.mean():.5f}")
+    assert t_same / t_ref >= 0.99, name
+    eng.close()
+
+
+def test_long_form_two_hours_yaml_vs_reference(seg):
+    """BASELINE.json configs[4] end to end: one 2 h stream (115.2 M samples, 360 windows, 359 640 frames),
+    decisive probabilities, dac / strm / pthr(+moving average) -> custom_segments.yaml, against the yaml the
+    UNMODIFIED reference produced for the same stream (tests/golden/speech_talk_2h.npz: full yaml text and
+    boundaries; probabilities as an every-8th-frame fp32 sample). Records are compared as text: a record is
+    identical iff its `duration` and `offset` strings are. >= 99 % of the records (and of the pDAC + pSTRM
+    boundaries) must be identical; byte identity of the whole file is reported."""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    g = load_gold("speech_talk_2h")
+    eng = _decisive_engine(g)
+    wave_f = speech_wave(int(g["n_samples"]), int(g["audio_seed"]))
+    res = TalkRunner(eng, batch_size=14, segment_sec=20, inference_times=1, device_batch=28).run([wave_f])[0]
+    assert len(res.probs) == int(g["n_frames"]) == 359_640
+    every = int(g["probs_every"])
+    err = np.abs(res.probs[::every] - g["probs_avg"].astype(np.float64))
+    assert err.max() <= PROB_TOL + 1e-6, err.max()
+    t_ref = t_same = 0
+    for tag, fn in (("dac", seg.pdac), ("strm", seg.strm), ("pthr", seg.pthr)):
+        segs = fn(res.probs, **ALGOS[tag])
+        text = yaml.dump(seg.update_yaml_content([], segs, "talk.wav"), default_flow_style=True)
+        ref_text = str(g[f"{tag}_yaml"])
+        got_recs = {(r["offset"], r["duration"]) for r in yaml.safe_load(text)}
+        ref_recs = [(r["offset"], r["duration"]) for r in yaml.safe_load(ref_text)]
+        same_recs = sum(1 for r in ref_recs if r in got_recs)
+        got = np.array([[s.start, s.end] for s in segs]).reshape(-1, 2)
+        ref = g[f"{tag}_bounds"]
+        exact = boundary_agreement(got, ref, tol=0.0)
+        print(f"PARITY 2h {tag}: {len(segs)} segments vs {len(ref)}; yaml records identical {same_recs}/{len(ref_recs)} "
+              f"({same_recs / len(ref_recs):.4f}); boundaries identical {exact:.4f}; whole file byte-identical: {text == ref_text}")
+        assert abs(len(segs) - len(ref)) <= max(1, len(ref) // 200), tag
+        assert same_recs / len(ref_recs) >= 0.99, tag
+        if tag != "pthr":
+            t_ref += ref.size
+            t_same += int(round(exact * ref.size))
+    print(f"PARITY 2h: pDAC+pSTRM {t_same}/{t_ref} boundaries identical ({t_same / t_ref:.4f}); "
+          f"max-abs prob err {err.max():.4f}, mean {err.mean():.5f}")
+    assert t_same / t_ref >= 0.99
+    eng.close()
 
 
 def test_dropin_modules_match_reference(tmp_path, tiny_engine):
@@ -339,6 +429,7 @@ def test_segment_cli_generate(tmp_path):
         f"ckpt_path={tmp_path / 'ckpt.pt'}", f"config_path={tmp_path / 'train.yaml'}", f"output_dir={tmp_path}",
         "algorithm=pthr", "infer_data=toy", f"infer_data.wav_dir={tmp_path}",
         f"infer_data.orig_seg_yaml={tmp_path / 'orig.yaml'}", "inference_times=2"])
+    cfg = cfglib.merge(cfglib.load(cfg.config_path), cfg)      # reference segment.py:161-163
     content = cli.generate(cfg)
     assert len(content) > 0 and set(content[0]) == {"duration", "offset", "rW", "uW", "speaker_id", "wav"}
     text = yaml.dump(content, default_flow_style=True)

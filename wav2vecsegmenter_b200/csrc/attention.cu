@@ -267,12 +267,10 @@ int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head
   if (head_dim == 64) {
     attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    W2V_ONCE_BEGIN
       W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr = true;
-    }
+    W2V_ONCE_END
     attention_kernel<128><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
   }
   W2V_CHECK_LAUNCH();

@@ -391,23 +391,19 @@ int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int h
   dim3 grid((R + AT_BM - 1) / AT_BM, heads, B);
   ProfScope ps(s, head_dim == 64 ? "attention_d64" : "attention_d128");
   if (head_dim == 64) {
-    static bool attr = false;
-    if (!attr) {
+    W2V_ONCE_BEGIN
       W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           AttCfg<64>::SMEM_BYTES));
-      attr = true;
-    }
+    W2V_ONCE_END
     attention_tc_kernel<64><<<grid, AT_THREADS, AttCfg<64>::SMEM_BYTES, s>>>(tm, R, heads, kv_len,
                                                                              scale_log2, ctx);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    W2V_ONCE_BEGIN
       W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<128>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           AttCfg<128>::SMEM_BYTES));
-      attr = true;
-    }
+    W2V_ONCE_END
     attention_tc_kernel<128><<<grid, AT_THREADS, AttCfg<128>::SMEM_BYTES, s>>>(tm, R, heads, kv_len,
                                                                                scale_log2, ctx);
   }

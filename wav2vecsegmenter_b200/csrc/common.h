@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/w2vseg.h"
 
 namespace w2v {
@@ -44,6 +46,17 @@ void count_launch(int n = 1);
       return W2VSEG_ERR_ARG;                                                                  \
     }                                                                                         \
   } while (0)
+
+// Runs the following block at least once per process, thread-safely: the guarded work (cudaFuncSetAttribute) is
+// idempotent, so two threads racing through it is harmless — only the flag itself must not be a data race.
+#define W2V_ONCE_BEGIN                                  \
+  {                                                     \
+    static std::atomic<int> _once_done{0};              \
+    if (_once_done.load(std::memory_order_acquire) == 0) {
+#define W2V_ONCE_END                                    \
+      _once_done.store(1, std::memory_order_release);   \
+    }                                                   \
+  }
 
 #define W2V_TRY(expr)                                                                         \
   do {                                                                                        \

@@ -362,12 +362,10 @@ int conv0_tc_launch(const float* audio, int64_t audio_stride, const int32_t* sam
   const __half* wp = reinterpret_cast<const __half*>(pack);
   const float* u = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(pack) +
                                                   (size_t)512 * 16 * sizeof(__half));
-  static bool attr_set = false;
-  if (!attr_set) {
+  W2V_ONCE_BEGIN
     W2V_CHECK_CUDA(cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C0T_SMEM));
-    attr_set = true;
-  }
+  W2V_ONCE_END
   const int fb_per_window = (R0 + C0T_ROWS - 1) / C0T_ROWS;
   const long long total = (long long)B * fb_per_window;
   W2V_REQUIRE(total < (1ll << 30), "conv0: too many frame blocks (%lld)", total);

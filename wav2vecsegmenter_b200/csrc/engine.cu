@@ -23,8 +23,12 @@ constexpr int kHalo = 64;  // pos-conv padding (128 // 2, HF:343)
 
 struct LNW { float* g = nullptr; float* b = nullptr; };
 
+// mean input (over the rows of the calibration batch) of every GEMM of a transformer layer
+struct LayerX { float* ln1 = nullptr; float* ctx = nullptr; float* ln2 = nullptr; float* mid = nullptr; };
+
 struct EncLayerW {
   LNW ln1, ln2;
+  LayerX x;
   bf16* wqkv = nullptr; float* bqkv = nullptr;
   bf16* wo = nullptr;   float* bo = nullptr;
   bf16* w1 = nullptr;   float* b1 = nullptr;   // [F1, D]: FFN-up rows, then adapter-down rows
@@ -36,6 +40,7 @@ struct EncLayerW {
 
 struct HeadW {
   LNW ln1, ln2, lnf;
+  LayerX x;
   bf16* win = nullptr; float* bin = nullptr;
   bf16* wo = nullptr;  float* bo = nullptr;
   bf16* w1 = nullptr;  float* b1 = nullptr;
@@ -59,7 +64,14 @@ struct Slot {
   int O = 0, I = 0, J = 0;
   bool optional = false;
   int alt_group = 0;  // slots sharing a non-zero alt_group: group satisfied by its 'primary' set
+  // bias correction (w2vseg_correct_bias): effective bias of this matrix's output rows, mean input of its
+  // columns (x_tap_stride > 0: grouped positional conv table [tap][channel])
+  float* c_bias = nullptr;
+  const float* c_x = nullptr;
+  int c_x_tap_stride = 0;
 };
+
+struct BiasPair { float* raw; float* eff; int n; };
 
 struct Workspace {
   float2* stats; int32_t* enc_len; int32_t* included; double2* stat_partial;
@@ -90,6 +102,13 @@ struct w2vseg_handle {
   std::map<std::string, Slot> slots;
   std::map<std::string, bool> was_set;
   bool finalized = false;
+  // bias correction state: GEMM biases exist as (raw, effective) pairs; finalize() resets eff = raw
+  std::vector<BiasPair> bias_pairs;
+  std::map<std::string, bool> corrected;
+  bool calibrated = false;
+  float* conv_x[7] = {};           // mean im2col row of conv layer l (k*512 floats)
+  float* fp_x = nullptr;           // mean input of the feature projection (512)
+  float* pos_x = nullptr;          // [taps][D]: mean of zpad rows shifted by tap
 
   template <typename T>
   T* alloc(size_t n) {
@@ -107,15 +126,26 @@ void add_vec(w2vseg_handle* h, const std::string& name, float** dst, int n, bool
   Slot s; s.kind = SLOT_VEC; s.numel = n; s.fdst = *dst; s.optional = optional;
   h->slots[name] = s;
 }
+// GEMM bias: `raw` receives the checkpoint values, the forward reads `eff` (= raw minus bias corrections)
+float* add_bias(w2vseg_handle* h, const std::string& name, float** eff, int n) {
+  float* raw = h->alloc<float>(n);
+  *eff = h->alloc<float>(n);
+  if (!name.empty()) {
+    Slot s; s.kind = SLOT_VEC; s.numel = n; s.fdst = raw;
+    h->slots[name] = s;
+  }
+  h->bias_pairs.push_back({raw, *eff, n});
+  return raw;
+}
 void add_ln(w2vseg_handle* h, const std::string& prefix, LNW* ln, int n) {
   add_vec(h, prefix + ".weight", &ln->g, n);
   add_vec(h, prefix + ".bias", &ln->b, n);
 }
 // matrix [rows, cols] packed into dst (+col offset / row offset already applied), leading dim ld
 void add_mat(w2vseg_handle* h, const std::string& name, bf16* dst, int rows, int cols, int64_t ld,
-             float scale = 1.f) {
+             float scale = 1.f, float* c_bias = nullptr, const float* c_x = nullptr) {
   Slot s; s.kind = SLOT_MAT; s.numel = (int64_t)rows * cols; s.bdst = dst; s.rows = rows;
-  s.cols = cols; s.ld = ld; s.scale = scale;
+  s.cols = cols; s.ld = ld; s.scale = scale; s.c_bias = c_bias; s.c_x = c_x;
   h->slots[name] = s;
 }
 
@@ -126,6 +156,7 @@ void build_layout(w2vseg_handle* h) {
   const int D = h->D, CD = c.conv_dim;
   h->arena_used = 0;
   h->slots.clear();
+  h->bias_pairs.clear();
 
   // feature extractor
   h->conv0_wt = h->alloc<float>((size_t)10 * CD);
@@ -136,26 +167,31 @@ void build_layout(w2vseg_handle* h) {
   }
   for (int l = 0; l < 7; ++l) {
     const std::string p = "fe.conv" + std::to_string(l);
-    add_vec(h, p + ".bias", &h->conv_b[l], CD);
+    if (l == 0) add_vec(h, p + ".bias", &h->conv_b[l], CD);   // folded into the fp16 pack of conv0_tc
+    else add_bias(h, p + ".bias", &h->conv_b[l], CD);
     add_ln(h, p + ".ln", &h->conv_ln[l], CD);
     if (l > 0) {
       h->conv_w[l] = h->alloc<bf16>((size_t)CD * CD * kConvK[l]);
+      h->conv_x[l] = h->alloc<float>((size_t)CD * kConvK[l]);
       Slot s; s.kind = SLOT_CONV; s.numel = (int64_t)CD * CD * kConvK[l]; s.bdst = h->conv_w[l];
-      s.O = CD; s.I = CD; s.J = kConvK[l];
+      s.O = CD; s.I = CD; s.J = kConvK[l]; s.c_bias = h->conv_b[l]; s.c_x = h->conv_x[l];
       h->slots[p + ".weight"] = s;
     }
   }
   // feature projection
   add_ln(h, "fp.ln", &h->fp_ln, CD);
   h->fp_w = h->alloc<bf16>((size_t)D * CD);
-  add_mat(h, "fp.proj.weight", h->fp_w, D, CD, CD);
-  add_vec(h, "fp.proj.bias", &h->fp_b, D);
+  h->fp_x = h->alloc<float>(CD);
+  add_bias(h, "fp.proj.bias", &h->fp_b, D);
+  add_mat(h, "fp.proj.weight", h->fp_w, D, CD, CD, 1.f, h->fp_b, h->fp_x);
   // positional conv: either (weight_g, weight_v) or an already folded weight
   const int gc = D / c.pos_groups;  // channels per group
   h->pos_g = h->alloc<float>(c.pos_kernel);
   h->pos_v = h->alloc<float>((size_t)D * gc * c.pos_kernel);
   h->pos_scale = h->alloc<float>(c.pos_kernel);
   h->pos_w = h->alloc<bf16>((size_t)D * gc * c.pos_kernel);
+  h->pos_x = h->alloc<float>((size_t)c.pos_kernel * D);
+  add_bias(h, "pos.bias", &h->pos_b, D);
   {
     Slot s; s.kind = SLOT_RAW; s.numel = c.pos_kernel; s.fdst = h->pos_g; s.alt_group = 1;
     h->slots["pos.weight_g"] = s;
@@ -163,10 +199,9 @@ void build_layout(w2vseg_handle* h) {
     v.alt_group = 1;
     h->slots["pos.weight_v"] = v;
     Slot w; w.kind = SLOT_CONV; w.numel = v.numel; w.bdst = h->pos_w; w.O = D; w.I = gc;
-    w.J = c.pos_kernel; w.alt_group = 2;
+    w.J = c.pos_kernel; w.alt_group = 2; w.c_bias = h->pos_b; w.c_x = h->pos_x; w.c_x_tap_stride = D;
     h->slots["pos.weight"] = w;
   }
-  add_vec(h, "pos.bias", &h->pos_b, D);
 
   // encoder layers
   h->enc.assign(c.n_layers, EncLayerW());
@@ -177,33 +212,35 @@ void build_layout(w2vseg_handle* h) {
     L.F1 = c.ffn + (L.adapter ? c.adapter_dim : 0);
     add_ln(h, p + ".ln1", &L.ln1, D);
     add_ln(h, p + ".ln2", &L.ln2, D);
+    L.x.ln1 = h->alloc<float>(D); L.x.ctx = h->alloc<float>(D); L.x.ln2 = h->alloc<float>(D);
+    L.x.mid = h->alloc<float>(L.F1);
     L.wqkv = h->alloc<bf16>((size_t)3 * D * D);
-    L.bqkv = h->alloc<float>((size_t)3 * D);
+    float* bqkv_raw = add_bias(h, "", &L.bqkv, 3 * D);
     const char* qkvn[3] = {".q", ".k", ".v"};
     for (int j = 0; j < 3; ++j) {
-      add_mat(h, p + qkvn[j] + ".weight", L.wqkv + (size_t)j * D * D, D, D, D);
-      Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.bqkv + (size_t)j * D;
+      add_mat(h, p + qkvn[j] + ".weight", L.wqkv + (size_t)j * D * D, D, D, D, 1.f, L.bqkv + (size_t)j * D, L.x.ln1);
+      Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = bqkv_raw + (size_t)j * D;
       h->slots[p + qkvn[j] + ".bias"] = s;
     }
     L.wo = h->alloc<bf16>((size_t)D * D);
-    add_mat(h, p + ".o.weight", L.wo, D, D, D);
-    add_vec(h, p + ".o.bias", &L.bo, D);
+    add_bias(h, p + ".o.bias", &L.bo, D);
+    add_mat(h, p + ".o.weight", L.wo, D, D, D, 1.f, L.bo, L.x.ctx);
     L.w1 = h->alloc<bf16>((size_t)L.F1 * D);
-    L.b1 = h->alloc<float>(L.F1);
+    float* b1_raw = add_bias(h, "", &L.b1, L.F1);
     L.w2 = h->alloc<bf16>((size_t)D * L.F1);
     L.b2_raw = h->alloc<float>(D);
     L.bu_raw = h->alloc<float>(D);
     L.b2 = h->alloc<float>(D);
-    add_mat(h, p + ".ff1.weight", L.w1, c.ffn, D, D);
-    { Slot s; s.kind = SLOT_VEC; s.numel = c.ffn; s.fdst = L.b1; h->slots[p + ".ff1.bias"] = s; }
-    add_mat(h, p + ".ff2.weight", L.w2, D, c.ffn, L.F1);
+    add_mat(h, p + ".ff1.weight", L.w1, c.ffn, D, D, 1.f, L.b1, L.x.ln2);
+    { Slot s; s.kind = SLOT_VEC; s.numel = c.ffn; s.fdst = b1_raw; h->slots[p + ".ff1.bias"] = s; }
+    add_mat(h, p + ".ff2.weight", L.w2, D, c.ffn, L.F1, 1.f, L.b2, L.x.mid);
     { Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.b2_raw; h->slots[p + ".ff2.bias"] = s; }
     if (L.adapter) {
       // y + s*(Wu relu(Wd u + bd) + bu)  ==  extra FFN hidden units with ReLU and weights s*Wu
-      add_mat(h, p + ".ad_down.weight", L.w1 + (size_t)c.ffn * D, c.adapter_dim, D, D);
-      { Slot s; s.kind = SLOT_VEC; s.numel = c.adapter_dim; s.fdst = L.b1 + c.ffn;
+      add_mat(h, p + ".ad_down.weight", L.w1 + (size_t)c.ffn * D, c.adapter_dim, D, D, 1.f, L.b1 + c.ffn, L.x.ln2);
+      { Slot s; s.kind = SLOT_VEC; s.numel = c.adapter_dim; s.fdst = b1_raw + c.ffn;
         h->slots[p + ".ad_down.bias"] = s; }
-      add_mat(h, p + ".ad_up.weight", L.w2 + c.ffn, D, c.adapter_dim, L.F1, c.adapter_scale);
+      add_mat(h, p + ".ad_up.weight", L.w2 + c.ffn, D, c.adapter_dim, L.F1, c.adapter_scale, L.b2, L.x.mid + c.ffn);
       { Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = L.bu_raw; h->slots[p + ".ad_up.bias"] = s; }
     }
   }
@@ -213,18 +250,20 @@ void build_layout(w2vseg_handle* h) {
     HeadW& H = h->head;
     add_ln(h, "head.ln1", &H.ln1, D);
     add_ln(h, "head.ln2", &H.ln2, D);
+    H.x.ln1 = h->alloc<float>(D); H.x.ctx = h->alloc<float>(D); H.x.ln2 = h->alloc<float>(D);
+    H.x.mid = h->alloc<float>(c.head_ffn);
     H.win = h->alloc<bf16>((size_t)3 * D * D);
-    add_mat(h, "head.in_proj.weight", H.win, 3 * D, D, D);
-    add_vec(h, "head.in_proj.bias", &H.bin, 3 * D);
+    add_bias(h, "head.in_proj.bias", &H.bin, 3 * D);
+    add_mat(h, "head.in_proj.weight", H.win, 3 * D, D, D, 1.f, H.bin, H.x.ln1);
     H.wo = h->alloc<bf16>((size_t)D * D);
-    add_mat(h, "head.o.weight", H.wo, D, D, D);
-    add_vec(h, "head.o.bias", &H.bo, D);
+    add_bias(h, "head.o.bias", &H.bo, D);
+    add_mat(h, "head.o.weight", H.wo, D, D, D, 1.f, H.bo, H.x.ctx);
     H.w1 = h->alloc<bf16>((size_t)c.head_ffn * D);
-    add_mat(h, "head.ff1.weight", H.w1, c.head_ffn, D, D);
-    add_vec(h, "head.ff1.bias", &H.b1, c.head_ffn);
+    add_bias(h, "head.ff1.bias", &H.b1, c.head_ffn);
+    add_mat(h, "head.ff1.weight", H.w1, c.head_ffn, D, D, 1.f, H.b1, H.x.ln2);
     H.w2 = h->alloc<bf16>((size_t)D * c.head_ffn);
-    add_mat(h, "head.ff2.weight", H.w2, D, c.head_ffn, c.head_ffn);
-    add_vec(h, "head.ff2.bias", &H.b2, D);
+    add_bias(h, "head.ff2.bias", &H.b2, D);
+    add_mat(h, "head.ff2.weight", H.w2, D, c.head_ffn, c.head_ffn, 1.f, H.b2, H.x.mid);
   }
   add_ln(h, "head.ln_f", &h->head.lnf, D);
   add_vec(h, "head.out.weight", &h->head.wout, D);
@@ -304,8 +343,10 @@ int check_ready(const w2vseg_handle* h) {
 }
 
 // ---- encoder: audio -> h (fp32 [B*R, D]) -------------------------------------------------------
+// calib: additionally record the mean input row of every GEMM (w2vseg_calibrate)
 int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_t audio_stride,
-                const int32_t* sample_len, const int32_t* norm_len, int B, int R, cudaStream_t st) {
+                const int32_t* sample_len, const int32_t* norm_len, int B, int R, cudaStream_t st,
+                bool calib = false) {
   const w2vseg_config& c = h->cfg;
   const int D = h->D, CD = c.conv_dim;
   const int64_t M = (int64_t)B * R;
@@ -328,6 +369,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.conv[l - 1], rows_out, kConvK[l] * CD, h->conv_w[l], CD, h->conv_b[l]);
     g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
     g.out = w.conv[l]; g.ld_out = CD;
+    if (calib) W2V_TRY(colmean_launch(w.conv[l - 1], 2 * CD, kConvK[l] * CD, 1, (int)rows_out, 0, h->conv_x[l], st));
     prof_tag(kConvK[l] == 3 ? "gemm.conv_k3" : "gemm.conv_k2");
     W2V_TRY(gemm_tc2_launch(g, st));
     prof_tag("ln_gelu.conv");
@@ -341,6 +383,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.feat, M, CD, h->fp_w, D, h->fp_b);
     g.out = w.h; g.ld_out = D; g.out_f32 = 1;
     g.mask_len = w.enc_len; g.mask_period = R;
+    if (calib) W2V_TRY(colmean_launch(w.feat, CD, CD, 1, (int)M, 0, h->fp_x, st));
     prof_tag("gemm.feat_proj");
     W2V_TRY(gemm_tc2_launch(g, st));
   }
@@ -352,6 +395,9 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     const int gc = D / c.pos_groups;
     W2V_REQUIRE(gc == 64, "positional conv: %d channels per group unsupported (64 only)", gc);
     GemmProblem g = posconv_problem(w.zpad, h->pos_w, h->pos_b, B, R, D, c.pos_kernel, w.h);
+    if (calib)   // tap j reads the rows shifted by j: one mean row per tap
+      for (int j = 0; j < c.pos_kernel; ++j)
+        W2V_TRY(colmean_launch(w.zpad + (size_t)j * D, D, D, B, R, R + 2 * kHalo, h->pos_x + (size_t)j * D, st));
     prof_tag("gemm.pos_conv");
     W2V_TRY(posconv_tc_launch(g, st));
   }
@@ -363,6 +409,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
       g.out = w.qkv; g.ld_out = 3 * D;
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln1, st));
       prof_tag("gemm.qkv");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -371,6 +418,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, L.x.ctx, st));
       prof_tag("gemm.attn_out");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -379,12 +427,14 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       GemmProblem g = linear(w.xn, M, D, L.w1, L.F1, L.b1);
       g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
       g.out = w.mid; g.ld_out = L.F1;
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln2, st));
       prof_tag("gemm.ffn_up");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, L.F1, L.w2, D, L.b2);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
+      if (calib) W2V_TRY(colmean_launch(w.mid, L.F1, L.F1, 1, (int)M, 0, L.x.mid, st));
       prof_tag("gemm.ffn_down");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -395,7 +445,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
 // ---- head: y (fp32 [B*R, D], updated in place) -> logits / probs --------------------------------
 int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const int32_t* out_len,
              float* logits, float* probs, cudaStream_t st, int64_t prob_stride = 0, int row_cols = 0,
-             int flag_col = -1) {
+             int flag_col = -1, bool calib = false) {
   const w2vseg_config& c = h->cfg;
   const int D = h->D;
   const int64_t M = (int64_t)B * R;
@@ -406,6 +456,7 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     {
       GemmProblem g = linear(w.xn, M, D, H.win, 3 * D, H.bin);
       g.out = w.qkv; g.ld_out = 3 * D;
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln1, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -413,6 +464,7 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     {
       GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, H.x.ctx, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -421,12 +473,14 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       GemmProblem g = linear(w.xn, M, D, H.w1, c.head_ffn, H.b1);
       g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
       g.out = w.mid; g.ld_out = c.head_ffn;
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln2, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, c.head_ffn, H.w2, D, H.b2);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
+      if (calib) W2V_TRY(colmean_launch(w.mid, c.head_ffn, c.head_ffn, 1, (int)M, 0, H.x.mid, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -516,6 +570,7 @@ int32_t w2vseg_set_weight(w2vseg_handle* h, const char* name, const float* src, 
   }
   h->was_set[name] = true;
   h->finalized = false;
+  h->calibrated = false;
   return 0;
 }
 
@@ -549,6 +604,10 @@ int32_t w2vseg_finalize_weights(w2vseg_handle* h, void* stream) {
     if (L.adapter) W2V_TRY(axpby_launch(L.b2_raw, 1.f, L.bu_raw, c.adapter_scale, L.b2, h->D, st));
     else W2V_TRY(axpby_launch(L.b2_raw, 1.f, nullptr, 0.f, L.b2, h->D, st));
   }
+  // effective GEMM biases = checkpoint values (any earlier bias correction is dropped)
+  for (const BiasPair& bp : h->bias_pairs) W2V_TRY(axpby_launch(bp.raw, 1.f, nullptr, 0.f, bp.eff, bp.n, st));
+  h->corrected.clear();
+  h->calibrated = false;
   h->finalized = true;
   return 0;
 }
@@ -567,6 +626,60 @@ static int check_ws(const w2vseg_handle* h, void* workspace, size_t workspace_by
   const size_t need = w->bytes + (size_t)(base - reinterpret_cast<uint8_t*>(workspace));
   W2V_REQUIRE(workspace_bytes >= need, "workspace too small: %zu bytes given, %zu needed (B=%d, R=%d)",
               workspace_bytes, need, B, R);
+  return 0;
+}
+
+int32_t w2vseg_calibrate(w2vseg_handle* h, const float* audio, int64_t audio_stride,
+                         const int32_t* sample_len, const int32_t* norm_len, const int32_t* out_len,
+                         int32_t B, int64_t l_max, void* workspace, size_t workspace_bytes, void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(audio && sample_len && norm_len && out_len, "calibrate: null argument");
+  W2V_REQUIRE(B > 0 && l_max >= 400 && audio_stride >= l_max, "calibrate: bad shape (B=%d, l_max=%lld)", B,
+              (long long)l_max);
+  if (!h->corrected.empty()) {
+    set_error("calibrate: biases already carry corrections; call w2vseg_finalize_weights first");
+    return W2VSEG_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = w2vseg_frame_stride(l_max);
+  Workspace w;
+  W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, /*calib*/ true));
+  W2V_TRY(run_head(h, w, w.h, B, R, out_len, nullptr, nullptr, st, 0, 0, -1, /*calib*/ true));
+  h->calibrated = true;
+  // the positional conv keeps its fp32 weight-norm factors in the handle: correct its bias right here
+  if (h->was_set.count("pos.weight_g") && h->was_set.count("pos.weight_v")) {
+    const int gc = h->D / h->cfg.pos_groups, J = h->cfg.pos_kernel;
+    W2V_TRY(bias_correct_launch(h->pos_v, h->pos_w, (int64_t)gc * J, h->D, gc * J, 1.f, 1, gc, J, h->pos_scale,
+                                h->pos_x, h->D, gc, h->pos_b, st));
+    h->corrected["pos.weight_v"] = true;
+  }
+  return 0;
+}
+
+int32_t w2vseg_correct_bias(w2vseg_handle* h, const char* name, const float* src, int64_t numel, void* stream) {
+  W2V_REQUIRE(h != nullptr && name != nullptr && src != nullptr, "correct_bias: null argument");
+  if (!h->finalized || !h->calibrated) {
+    set_error("correct_bias: needs finalised weights and a w2vseg_calibrate pass");
+    return W2VSEG_ERR_STATE;
+  }
+  auto it = h->slots.find(name);
+  W2V_REQUIRE(it != h->slots.end(), "correct_bias: unknown tensor name '%s'", name);
+  const Slot& s = it->second;
+  W2V_REQUIRE(numel == s.numel, "correct_bias: '%s' has %lld elements, expected %lld", name, (long long)numel,
+              (long long)s.numel);
+  if (s.c_bias == nullptr || (s.kind != SLOT_MAT && s.kind != SLOT_CONV)) return 0;   // nothing rounded to bf16
+  if (h->corrected.count(name)) {
+    set_error("correct_bias: '%s' was already corrected for this set of weights", name);
+    return W2VSEG_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s.kind == SLOT_MAT)
+    W2V_TRY(bias_correct_launch(src, s.bdst, s.ld, s.rows, s.cols, s.scale, 0, 0, 0, nullptr, s.c_x, 0, 1, s.c_bias, st));
+  else
+    W2V_TRY(bias_correct_launch(src, s.bdst, (int64_t)s.I * s.J, s.O, s.I * s.J, 1.f, 1, s.I, s.J, nullptr, s.c_x,
+                                s.c_x_tap_stride, s.I, s.c_bias, st));
+  h->corrected[name] = true;
   return 0;
 }
 
@@ -694,7 +807,10 @@ int32_t w2vseg_conv_gemm(const void* x, int64_t rows_out, int32_t C, int32_t kw,
   GemmProblem g = linear((const bf16*)x, rows_out, kw * C, (const bf16*)W, N, bias);
   g.a_row_stride = (int64_t)stride * C;
   g.out = out; g.ld_out = N;
-  return gemm_tc_launch(g, N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64), (cudaStream_t)stream);
+  // N % 256 == 0 (the feature extractor: N = 512): the CTA-pair kernel the forward pass itself runs on this
+  // overlapping-row view; other widths fall back to the single-CTA kernel
+  if (N % 256 == 0) return gemm_tc2_launch(g, (cudaStream_t)stream);
+  return gemm_tc_launch(g, N % 128 == 0 ? 128 : 64, (cudaStream_t)stream);
 }
 
 int32_t w2vseg_posconv(const void* zpad, const void* W, const float* bias, int32_t B, int32_t R, int32_t D,

@@ -241,12 +241,10 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   a.out = g.out; a.ld_out = g.ld_out; a.out_f32 = g.out_f32;
   a.mask_len = g.mask_len; a.mask_period = g.mask_period > 0 ? g.mask_period : 1;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  W2V_ONCE_BEGIN
+  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  W2V_ONCE_END
   const long long num_tiles = (long long)a.num_groups * a.tiles_m_per_group * (g.N / BLOCK_N);
   if (num_tiles == 0) return 0;
   const long long max_clusters = num_sms() / 2;

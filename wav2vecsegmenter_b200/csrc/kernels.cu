@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -470,6 +472,54 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, int O, int I, in
   dst[i] = __float2bfloat16_rn(v);
 }
 
+// ---- bias correction for the bf16 weight rounding (post-training-quantisation style) --------------
+// column sums of a bf16 row view: xsum[k] += sum over the block's rows of A[(g*group_stride + r)*row_stride + k]
+// (groups of rows_per_group rows; row_stride may be smaller than K: im2col view of a strided conv)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ A, long long row_stride, int K, int num_groups,
+              int rows_per_group, long long group_stride, float inv_rows, float* __restrict__ xmean) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  const long long total = (long long)num_groups * rows_per_group;
+  const long long per = (total + gridDim.y - 1) / gridDim.y;
+  const long long r0 = per * blockIdx.y, r1 = min(total, r0 + per);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const long long g = r / rows_per_group, t = r - g * rows_per_group;
+    acc += __bfloat162float(A[(g * group_stride + t) * row_stride + k]);
+  }
+  atomicAdd(xmean + k, acc * inv_rows);
+}
+
+// bias[n] -= sum_k (stored_bf16[n, k] - exact[n, k]) * xmean[xoff(n) + k], one warp per output row n.
+//   layout 0: exact[n, k] = src[n*K + k] * scale                     (Linear: src [N, K])
+//   layout 1: k = j*I + i, exact = src[(n*I + i)*J + j] * tap_scale[j]   (Conv1d weight [N, I, J] packed [N, J*I])
+// x_group_stride: xmean offset per group of `x_rows_per_group` output rows (grouped positional conv: the
+// mean of tap j, channel (n / gc) * gc + i sits at xmean[j * x_tap_stride + (n / gc) * gc + i])
+__global__ void __launch_bounds__(256)
+bias_correct_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ packed, long long ld,
+                    int N, int K, float scale, int layout, int I, int J, const float* __restrict__ tap_scale,
+                    const float* __restrict__ xmean, int x_tap_stride, int gc, float* __restrict__ bias) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float exact, x;
+    if (layout == 0) {
+      exact = src[(long long)n * K + k] * scale;
+      x = xmean[k];
+    } else {
+      const int j = k / I, i = k - j * I;
+      exact = src[((long long)n * I + i) * J + j] * (tap_scale != nullptr ? tap_scale[j] : 1.f);
+      x = x_tap_stride > 0 ? xmean[(long long)j * x_tap_stride + (n / gc) * gc + i] : xmean[k];
+    }
+    acc = fmaf(__bfloat162float(packed[(long long)n * ld + k]) - exact, x, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) bias[n] -= acc;
+}
+
 __global__ void transpose_f32_kernel(const float* __restrict__ src, int O, int J,
                                      float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -697,6 +747,29 @@ int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_sca
                      __nv_bfloat16* dst, cudaStream_t s) {
   const long long n = (long long)O * I * J;
   pack_conv_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, O, I, J, tap_scale, dst);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int colmean_launch(const __nv_bfloat16* A, int64_t row_stride, int K, int num_groups, int rows_per_group,
+                   int64_t group_stride, float* xmean, cudaStream_t s) {
+  const long long total = (long long)num_groups * rows_per_group;
+  if (total <= 0 || K <= 0) return 0;
+  W2V_CHECK_CUDA(cudaMemsetAsync(xmean, 0, sizeof(float) * K, s));
+  const int slabs = (int)std::min<long long>(64, (total + 255) / 256);
+  dim3 grid(blocks_for(K, 256), slabs);
+  colsum_kernel<<<grid, 256, 0, s>>>(A, row_stride, K, num_groups, rows_per_group, group_stride,
+                                     1.f / (float)total, xmean);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int bias_correct_launch(const float* src, const __nv_bfloat16* packed, int64_t ld, int N, int K, float scale,
+                        int layout, int I, int J, const float* tap_scale, const float* xmean,
+                        int x_tap_stride, int gc, float* bias, cudaStream_t s) {
+  if (N <= 0 || K <= 0) return 0;
+  bias_correct_kernel<<<blocks_for(N, 8), 256, 0, s>>>(src, packed, ld, N, K, scale, layout, I, J, tap_scale,
+                                                       xmean, x_tap_stride, gc, bias);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -68,6 +68,14 @@ int pack_matrix_launch(const float* src, int rows, int cols, float scale, __nv_b
 // conv weight [O, I, J] fp32 -> [O, J*I] bf16 (K index = j*I + i), optional per-tap scale[j]
 int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_scale,
                      __nv_bfloat16* dst, cudaStream_t s);
+// ---- bias correction for bf16 weight rounding (engine.cu: w2vseg_calibrate / w2vseg_correct_bias)
+// xmean[k] = mean over num_groups x rows_per_group rows of the bf16 view A (row g*group_stride + t, stride row_stride)
+int colmean_launch(const __nv_bfloat16* A, int64_t row_stride, int K, int num_groups, int rows_per_group,
+                   int64_t group_stride, float* xmean, cudaStream_t s);
+// bias[n] -= sum_k (packed_bf16[n, k] - exact_fp32[n, k]) * xmean[...]  (layouts: see kernels.cu)
+int bias_correct_launch(const float* src, const __nv_bfloat16* packed, int64_t ld, int N, int K, float scale,
+                        int layout, int I, int J, const float* tap_scale, const float* xmean,
+                        int x_tap_stride, int gc, float* bias, cudaStream_t s);
 // [O, J] fp32 -> [J, O] fp32 (conv layer 0 taps)
 int transpose_f32_launch(const float* src, int O, int J, float* dst, cudaStream_t s);
 // dst[i] = a[i] * sa + (b ? b[i] * sb : 0)

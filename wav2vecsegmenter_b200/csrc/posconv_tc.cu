@@ -229,12 +229,10 @@ int posconv_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   a.resid = g.resid; a.ld_resid = g.ld_resid;
   a.out = g.out; a.ld_out = g.ld_out; a.out_f32 = 1;
   a.mask_len = g.mask_len; a.mask_period = g.mask_period > 0 ? g.mask_period : 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  W2V_ONCE_BEGIN
     W2V_CHECK_CUDA(cudaFuncSetAttribute(posconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         PC_SMEM_BYTES));
-    attr_set = true;
-  }
+  W2V_ONCE_END
   const long long num_tiles = (long long)a.num_groups * a.tiles_m_per_group * (g.N / PC_BN);
   if (num_tiles == 0) return 0;
   const int grid = (int)(num_tiles < (long long)num_sms() ? num_tiles : (long long)num_sms());

@@ -7,6 +7,7 @@ Reference boundary this mirrors: lib/models.py:172-235 (SHAS), lib/evaluate.py:5
 """
 from __future__ import annotations
 
+import os
 import re
 
 import torch
@@ -73,6 +74,7 @@ class SFCEngine:
         self._h = h
         self._ws = None
         self._finalized = False
+        self._matrices = {}     # canonical name -> fp32 source tensor of every matrix uploaded since the last finalize
 
     def close(self):
         if getattr(self, "_h", None):
@@ -98,6 +100,8 @@ class SFCEngine:
         # src may be a temporary: the packing kernel is queued on the current stream, and the
         # caching allocator only reuses the block for later work on that same stream -> safe.
         self._finalized = False
+        if t.dim() >= 2:
+            self._matrices[name] = t
 
     def load_encoder_state(self, sd: dict, prefix: str = "wav2vec_model.model."):
         """HF Wav2Vec2Model parameters (keys after `prefix`); layers >= keep_layers are ignored
@@ -134,9 +138,38 @@ class SFCEngine:
         self.load_head_state(sd, "seg_model.")
         self.finalize()
 
-    def finalize(self):
+    def finalize(self, bias_correction: bool | None = None):
+        """completeness check + weight folding; then (default on, W2VSEG_BIAS_CORRECTION=0 turns it off)
+        the bias correction for the bf16 rounding of the matrices (include/w2vseg.h): one calibration
+        forward over a fixed synthetic speech-like signal + one small kernel per matrix."""
         nat.check(self.lib.w2vseg_finalize_weights(self._h, self._stream()), "finalize_weights")
         self._finalized = True
+        if bias_correction is None:
+            bias_correction = os.environ.get("W2VSEG_BIAS_CORRECTION", "1") != "0"
+        if bias_correction:
+            self.correct_biases()
+        self._matrices = {}
+
+    def correct_biases(self, calib_audio: torch.Tensor | None = None):
+        """calib_audio: fp32 [B, L] raw samples on any device (default: two 20 s windows of seeded noise
+        bursts and pauses, wav2vecsegmenter_b200.synth.speech_like_audio, seeds unrelated to any test)"""
+        from .synth import speech_like_audio
+
+        if calib_audio is None:
+            L = 320_000
+            calib_audio = torch.stack([speech_like_audio(L, 7770 + i)[0] for i in range(2)])
+        audio = calib_audio.to(self.device, torch.float32).contiguous()
+        B, L = audio.shape
+        lens = torch.full((B,), L, dtype=torch.int32, device=self.device)
+        out_len = torch.full((B,), self.num_frames(L), dtype=torch.int32, device=self.device)
+        ws = self._workspace(B, L)
+        nat.check(self.lib.w2vseg_calibrate(self._h, audio.data_ptr(), audio.stride(0), lens.data_ptr(), lens.data_ptr(),
+                                            out_len.data_ptr(), B, L, ws.data_ptr(), ws.numel(), self._stream()),
+                  "w2vseg_calibrate")
+        for name, t in self._matrices.items():
+            src = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            nat.check(self.lib.w2vseg_correct_bias(self._h, name.encode(), src.data_ptr(), src.numel(), self._stream()),
+                      f"correct_bias({name})")
 
     # ------------------------------------------------------------------ geometry / scratch
     def frame_stride(self, l_max: int) -> int:

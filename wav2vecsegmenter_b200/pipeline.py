@@ -333,8 +333,11 @@ class TalkRunner:
             side = self._side_stream = torch.cuda.Stream(self.engine.device)
         return side
 
-    def run(self, waves: list[np.ndarray]) -> list[TalkResult]:
-        """waves: one float32 array of raw samples per talk. Returns per-talk probabilities."""
+    def run(self, waves: list[np.ndarray], results_on: int | None = None) -> list[TalkResult] | None:
+        """waves: one float32 array of raw samples per talk. Returns per-talk probabilities.
+        With a process group, windows are sharded over the ranks and the probability rows are gathered;
+        `results_on=r` makes only rank r assemble the talks and copy them to the host (what segment.py
+        needs: rank 0 writes the yaml) — the other ranks return None and skip that work."""
         import torch
 
         eng = self.engine
@@ -353,14 +356,15 @@ class TalkRunner:
             if w.talk not in waves_dev:   # windows are talk-major, tiling-major: the first one starts lowest
                 first = min(x.start for x in wins[lo:hi] if x.talk == w.talk)
                 waves_dev[w.talk] = LazyWave(waves[w.talk], eng.device, side, lo=first)
-        ev, batch_meta, plans = self._stage_meta(wins[lo:hi], wins, n_frames, side)
+        mine = results_on is None or results_on == rank      # does this rank assemble the talks?
+        ev, batch_meta, plans = self._stage_meta(wins[lo:hi], wins if mine else [], n_frames, side)
         torch.cuda.current_stream(eng.device).wait_event(ev)
         rows = self._forward_rows(waves_dev, wins[lo:hi], r_max, batch_meta)
         for lw in waves_dev.values():
             lw.buf.record_stream(torch.cuda.current_stream(eng.device))
         if world > 1:
             rows = gather_rows(rows, len(wins), world, self.dist_group)
-        return self.reduce(rows, wins, n_frames, plans)
+        return self.reduce(rows, wins, n_frames, plans) if mine else None
 
     def reduce_device(self, rows, wins: list[Window], n_frames: list[int], plans=None):
         """rows [len(wins), r] (device) -> per talk (avg float64 [n], tilings float64 [inference_times, n]) on
@@ -388,9 +392,29 @@ class TalkRunner:
         return out
 
     def reduce(self, rows, wins: list[Window], n_frames: list[int], plans=None) -> list[TalkResult]:
-        """rows [len(wins), r] (device) -> per-talk averaged probabilities on the host"""
-        return [TalkResult(avg.cpu().numpy(), [til[i].cpu().numpy() for i in range(self.inference_times)])
-                for avg, til in self.reduce_device(rows, wins, n_frames, plans)]
+        """rows [len(wins), r] (device) -> per-talk averaged probabilities on the host. All reduction
+        kernels are queued first; the results then leave in ONE pass of async copies into one pinned
+        buffer and one synchronisation (a `.cpu()` per talk and tiling costs a device sync each)."""
+        import torch
+
+        dev = self.reduce_device(rows, wins, n_frames, plans)
+        it = self.inference_times
+        total = sum(n for n in n_frames) * (1 + (it if it > 1 else 0))
+        host = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
+        out, off = [], 0
+        for (avg, til), n in zip(dev, n_frames):
+            a = host[off: off + n]
+            a.copy_(avg, non_blocking=True)
+            off += n
+            parts = [a]
+            if it > 1:
+                t = host[off: off + it * n].view(it, n)
+                t.copy_(til, non_blocking=True)
+                off += it * n
+                parts = [t[i] for i in range(it)]
+            out.append((a, parts))
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return [TalkResult(a.numpy(), [p.numpy() for p in parts]) for a, parts in out]
 
     def run_stream(self, talks, depth: int = 2):
         """Throughput API: yields one TalkResult per input talk (same values as run([wave])[0]), with a
