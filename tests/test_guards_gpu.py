@@ -88,3 +88,23 @@ def test_reductions_stay_inside_their_buffers():
     nat.check(lib.w2vseg_overlap_average(talk.ptr, 1, n, out.ptr, st), "overlap_average")
     torch.cuda.synchronize()
     assert talk.intact() and out.intact()
+
+
+def test_two_handles_same_weights_bit_identical():
+    """weight packing, folding and the bias-correction calibration are deterministic: two handles (as on
+    two ranks of a multi-GPU job) loaded with the same checkpoint give bit-identical probabilities"""
+    spec = synth.TINY
+    sd = synth.random_state_dict(spec, 3)
+    lens = [64000, 50000]
+    audio = torch.zeros(2, 64000)
+    for i, n in enumerate(lens):
+        audio[i, :n] = synth.synthetic_audio(n, 300 + i)
+    audio = audio.cuda()
+    outs = []
+    for _ in range(2):
+        eng = SFCEngine(spec)
+        eng.load_state_dict(sd)
+        _, p = eng.sfc_forward(audio, lens, [64000, 64000], [eng.num_frames(n) for n in lens], 64000)
+        outs.append(p.cpu())
+        eng.close()
+    assert torch.equal(outs[0], outs[1])

@@ -20,6 +20,7 @@ namespace {
 
 constexpr int kConvK[7] = {10, 3, 3, 3, 3, 2, 2};
 constexpr int kHalo = 64;  // pos-conv padding (128 // 2, HF:343)
+constexpr size_t kCalibScratch = 64 * 8192;  // floats: row-slab partial sums of the calibration pass
 
 struct LNW { float* g = nullptr; float* b = nullptr; };
 
@@ -109,6 +110,7 @@ struct w2vseg_handle {
   float* conv_x[7] = {};           // mean im2col row of conv layer l (k*512 floats)
   float* fp_x = nullptr;           // mean input of the feature projection (512)
   float* pos_x = nullptr;          // [taps][D]: mean of zpad rows shifted by tap
+  float* calib_scratch = nullptr;  // kCalibScratch floats
 
   template <typename T>
   T* alloc(size_t n) {
@@ -158,6 +160,7 @@ void build_layout(w2vseg_handle* h) {
   h->slots.clear();
   h->bias_pairs.clear();
 
+  h->calib_scratch = h->alloc<float>(kCalibScratch);
   // feature extractor
   h->conv0_wt = h->alloc<float>((size_t)10 * CD);
   h->conv0_pack = h->alloc<uint8_t>(conv0_tc_pack_bytes());
@@ -369,7 +372,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.conv[l - 1], rows_out, kConvK[l] * CD, h->conv_w[l], CD, h->conv_b[l]);
     g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
     g.out = w.conv[l]; g.ld_out = CD;
-    if (calib) W2V_TRY(colmean_launch(w.conv[l - 1], 2 * CD, kConvK[l] * CD, 1, (int)rows_out, 0, h->conv_x[l], st));
+    if (calib) W2V_TRY(colmean_launch(w.conv[l - 1], 2 * CD, kConvK[l] * CD, 1, (int)rows_out, 0, h->conv_x[l], h->calib_scratch, kCalibScratch, st));
     prof_tag(kConvK[l] == 3 ? "gemm.conv_k3" : "gemm.conv_k2");
     W2V_TRY(gemm_tc2_launch(g, st));
     prof_tag("ln_gelu.conv");
@@ -383,7 +386,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.feat, M, CD, h->fp_w, D, h->fp_b);
     g.out = w.h; g.ld_out = D; g.out_f32 = 1;
     g.mask_len = w.enc_len; g.mask_period = R;
-    if (calib) W2V_TRY(colmean_launch(w.feat, CD, CD, 1, (int)M, 0, h->fp_x, st));
+    if (calib) W2V_TRY(colmean_launch(w.feat, CD, CD, 1, (int)M, 0, h->fp_x, h->calib_scratch, kCalibScratch, st));
     prof_tag("gemm.feat_proj");
     W2V_TRY(gemm_tc2_launch(g, st));
   }
@@ -397,7 +400,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = posconv_problem(w.zpad, h->pos_w, h->pos_b, B, R, D, c.pos_kernel, w.h);
     if (calib)   // tap j reads the rows shifted by j: one mean row per tap
       for (int j = 0; j < c.pos_kernel; ++j)
-        W2V_TRY(colmean_launch(w.zpad + (size_t)j * D, D, D, B, R, R + 2 * kHalo, h->pos_x + (size_t)j * D, st));
+        W2V_TRY(colmean_launch(w.zpad + (size_t)j * D, D, D, B, R, R + 2 * kHalo, h->pos_x + (size_t)j * D, h->calib_scratch, kCalibScratch, st));
     prof_tag("gemm.pos_conv");
     W2V_TRY(posconv_tc_launch(g, st));
   }
@@ -409,7 +412,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
       g.out = w.qkv; g.ld_out = 3 * D;
-      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln1, st));
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln1, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.qkv");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -418,7 +421,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     {
       GemmProblem g = linear(w.ctx, M, D, L.wo, D, L.bo);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
-      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, L.x.ctx, st));
+      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, L.x.ctx, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.attn_out");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -427,14 +430,14 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       GemmProblem g = linear(w.xn, M, D, L.w1, L.F1, L.b1);
       g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
       g.out = w.mid; g.ld_out = L.F1;
-      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln2, st));
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, L.x.ln2, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.ffn_up");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, L.F1, L.w2, D, L.b2);
       g.resid = w.h; g.ld_resid = D; g.out = w.h; g.ld_out = D; g.out_f32 = 1;
-      if (calib) W2V_TRY(colmean_launch(w.mid, L.F1, L.F1, 1, (int)M, 0, L.x.mid, st));
+      if (calib) W2V_TRY(colmean_launch(w.mid, L.F1, L.F1, 1, (int)M, 0, L.x.mid, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.ffn_down");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -456,7 +459,7 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     {
       GemmProblem g = linear(w.xn, M, D, H.win, 3 * D, H.bin);
       g.out = w.qkv; g.ld_out = 3 * D;
-      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln1, st));
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln1, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -464,7 +467,7 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
     {
       GemmProblem g = linear(w.ctx, M, D, H.wo, D, H.bo);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
-      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, H.x.ctx, st));
+      if (calib) W2V_TRY(colmean_launch(w.ctx, D, D, 1, (int)M, 0, H.x.ctx, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
@@ -473,14 +476,14 @@ int run_head(w2vseg_handle* h, const Workspace& w, float* y, int B, int R, const
       GemmProblem g = linear(w.xn, M, D, H.w1, c.head_ffn, H.b1);
       g.act_lo = ACT_GELU; g.act_hi = ACT_GELU;
       g.out = w.mid; g.ld_out = c.head_ffn;
-      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln2, st));
+      if (calib) W2V_TRY(colmean_launch(w.xn, D, D, 1, (int)M, 0, H.x.ln2, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
     {
       GemmProblem g = linear(w.mid, M, c.head_ffn, H.w2, D, H.b2);
       g.resid = y; g.ld_resid = D; g.out = y; g.ld_out = D; g.out_f32 = 1;
-      if (calib) W2V_TRY(colmean_launch(w.mid, c.head_ffn, c.head_ffn, 1, (int)M, 0, H.x.mid, st));
+      if (calib) W2V_TRY(colmean_launch(w.mid, c.head_ffn, c.head_ffn, 1, (int)M, 0, H.x.mid, h->calib_scratch, kCalibScratch, st));
       prof_tag("gemm.head");
       W2V_TRY(gemm_tc2_launch(g, st));
     }

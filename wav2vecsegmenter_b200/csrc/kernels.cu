@@ -473,11 +473,13 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, int O, int I, in
 }
 
 // ---- bias correction for the bf16 weight rounding (post-training-quantisation style) --------------
-// column sums of a bf16 row view: xsum[k] += sum over the block's rows of A[(g*group_stride + r)*row_stride + k]
-// (groups of rows_per_group rows; row_stride may be smaller than K: im2col view of a strided conv)
+// column means of a bf16 row view in two DETERMINISTIC passes (no atomics: every rank of a multi-GPU job must
+// derive bit-identical corrections): partial[slab][k] = sum over the slab's rows of A[(g*group_stride + t)*row_stride + k]
+// (groups of rows_per_group rows; row_stride may be smaller than K: im2col view of a strided conv), then
+// xmean[k] = (sum over slabs in order) / rows.
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ A, long long row_stride, int K, int num_groups,
-              int rows_per_group, long long group_stride, float inv_rows, float* __restrict__ xmean) {
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ A, long long row_stride, int K, int num_groups,
+                      int rows_per_group, long long group_stride, float* __restrict__ partial) {
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k >= K) return;
   const long long total = (long long)num_groups * rows_per_group;
@@ -488,7 +490,15 @@ colsum_kernel(const __nv_bfloat16* __restrict__ A, long long row_stride, int K, 
     const long long g = r / rows_per_group, t = r - g * rows_per_group;
     acc += __bfloat162float(A[(g * group_stride + t) * row_stride + k]);
   }
-  atomicAdd(xmean + k, acc * inv_rows);
+  partial[(long long)blockIdx.y * K + k] = acc;
+}
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int K, int slabs, float inv_rows, float* __restrict__ xmean) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int s = 0; s < slabs; ++s) acc += partial[(long long)s * K + k];
+  xmean[k] = acc * inv_rows;
 }
 
 // bias[n] -= sum_k (stored_bf16[n, k] - exact[n, k]) * xmean[xoff(n) + k], one warp per output row n.
@@ -752,14 +762,16 @@ int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_sca
 }
 
 int colmean_launch(const __nv_bfloat16* A, int64_t row_stride, int K, int num_groups, int rows_per_group,
-                   int64_t group_stride, float* xmean, cudaStream_t s) {
+                   int64_t group_stride, float* xmean, float* scratch, size_t scratch_floats, cudaStream_t s) {
   const long long total = (long long)num_groups * rows_per_group;
   if (total <= 0 || K <= 0) return 0;
-  W2V_CHECK_CUDA(cudaMemsetAsync(xmean, 0, sizeof(float) * K, s));
-  const int slabs = (int)std::min<long long>(64, (total + 255) / 256);
+  int slabs = (int)std::min<long long>(64, (total + 255) / 256);
+  slabs = (int)std::min<long long>(slabs, (long long)(scratch_floats / (size_t)K));
+  W2V_REQUIRE(slabs >= 1, "colmean: scratch of %zu floats too small for K=%d", scratch_floats, K);
   dim3 grid(blocks_for(K, 256), slabs);
-  colsum_kernel<<<grid, 256, 0, s>>>(A, row_stride, K, num_groups, rows_per_group, group_stride,
-                                     1.f / (float)total, xmean);
+  colsum_partial_kernel<<<grid, 256, 0, s>>>(A, row_stride, K, num_groups, rows_per_group, group_stride, scratch);
+  W2V_CHECK_LAUNCH();
+  colsum_final_kernel<<<blocks_for(K, 256), 256, 0, s>>>(scratch, K, slabs, 1.f / (float)total, xmean);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -70,8 +70,9 @@ int pack_conv_launch(const float* src, int O, int I, int J, const float* tap_sca
                      __nv_bfloat16* dst, cudaStream_t s);
 // ---- bias correction for bf16 weight rounding (engine.cu: w2vseg_calibrate / w2vseg_correct_bias)
 // xmean[k] = mean over num_groups x rows_per_group rows of the bf16 view A (row g*group_stride + t, stride row_stride)
+// (two deterministic passes through `scratch`, >= K floats; more scratch = more row slabs in parallel)
 int colmean_launch(const __nv_bfloat16* A, int64_t row_stride, int K, int num_groups, int rows_per_group,
-                   int64_t group_stride, float* xmean, cudaStream_t s);
+                   int64_t group_stride, float* xmean, float* scratch, size_t scratch_floats, cudaStream_t s);
 // bias[n] -= sum_k (packed_bf16[n, k] - exact_fp32[n, k]) * xmean[...]  (layouts: see kernels.cu)
 int bias_correct_launch(const float* src, const __nv_bfloat16* packed, int64_t ld, int N, int K, float scale,
                         int layout, int I, int J, const float* tap_scale, const float* xmean,
