@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define W2VSEG_ABI_VERSION 1
+#define W2VSEG_ABI_VERSION 2
 
 #define W2VSEG_OK 0
 #define W2VSEG_ERR_ARG (-1)    /* bad argument / shape */
@@ -68,6 +68,13 @@ typedef struct w2vseg_config {
   int32_t head_heads;        /* n_transformer_enc_heads: 8 (head_dim must be 128 or 64)       */
   int32_t head_ffn;          /* 2048 (torch.nn.TransformerEncoderLayer default)               */
   float ln_eps;              /* 1e-5                                                          */
+  /* feature-extractor variant (HF Wav2Vec2Config.feat_extract_norm / conv_bias):
+   *   feat_group_norm = 0: LayerNorm + GELU after each of the 7 convs (XLS-R, HF:275-299)
+   *   feat_group_norm = 1: GroupNorm(512 groups, i.e. per channel over time) + GELU after conv 0,
+   *                        GELU only after conv 1..6 (HF:302-323, 249-272); then fe.conv{1..6}.ln.* do not exist
+   *   conv_bias = 0: the convs have no bias (fe.conv{l}.bias do not exist)                     */
+  int32_t feat_group_norm;
+  int32_t conv_bias;
 } w2vseg_config;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -100,6 +107,7 @@ void w2vseg_destroy(w2vseg_handle* h);
  * state-dict layout of that parameter; `numel` is checked against the expected size.
  * Canonical names (i = layer index, l = conv layer 0..6):
  *   fe.conv{l}.weight [512,Cin,k]  fe.conv{l}.bias  fe.conv{l}.ln.weight  fe.conv{l}.ln.bias
+ *     (fe.conv0.ln.* = the GroupNorm affine when feat_group_norm = 1)
  *   fp.ln.weight  fp.ln.bias  fp.proj.weight [1024,512]  fp.proj.bias
  *   pos.weight_g [1,1,128]  pos.weight_v [1024,64,128]  (or pos.weight, already folded)  pos.bias
  *   enc.{i}.ln1.{weight,bias}  enc.{i}.{q,k,v,o}.{weight,bias}  enc.{i}.ln2.{weight,bias}

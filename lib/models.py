@@ -10,6 +10,7 @@ Inference only: there is no autograd through the CUDA path and no CPU fallback.
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 
 import torch
@@ -32,23 +33,33 @@ class _EngineHolder:
         self.engine: SFCEngine | None = None
         self.pending: dict = {}
         self.dirty = False
+        self.device = None
 
-    def create(self, device=None) -> SFCEngine:
-        """engine (device arena, no weights yet). `.to(device)` stops here: the reference moves the
-        module BEFORE it loads the checkpoint (segment.py:41-51), so with a frozen encoder the head
-        weights are still missing at this point."""
-        if self.engine is None:
-            dev = torch.device(device if device is not None else "cuda:0")
-            if dev.type != "cuda":
-                raise RuntimeError("lib.models.SHAS (B200 build) runs on CUDA only: there is no CPU path")
-            self.engine = SFCEngine(self.spec, dev)
-            self.dirty = True
-        return self.engine
+    def create(self, device=None) -> None:
+        """`.to(device)`: only remembers the device. The reference moves the module BEFORE it loads the
+        checkpoint (segment.py:41-51); the engine itself is built by the first forward / `.engine` access,
+        when the weights — and with them the feature-extractor variant (LayerNorm vs GroupNorm convs, conv
+        bias or not: HF config.feat_extract_norm / conv_bias) — are known."""
+        dev = torch.device(device if device is not None else "cuda:0")
+        if dev.type != "cuda":
+            raise RuntimeError("lib.models.SHAS (B200 build) runs on CUDA only: there is no CPU path")
+        self.device = dev
 
     def ensure(self, device=None) -> SFCEngine:
         """engine with every pending weight uploaded and finalised: called by the first forward /
         `.engine` access, i.e. after load_state_dict. Missing tensors surface here (W2VSegError)."""
-        eng = self.create(device)
+        if self.engine is None:
+            if device is not None or self.device is None:
+                self.create(device)
+            fe = "wav2vec_model.model.feature_extractor.conv_layers."
+            if any(k.startswith(fe) for k in self.pending):      # variant as the checkpoint has it
+                self.spec = dataclasses.replace(
+                    self.spec,
+                    feat_norm="layer" if fe + "1.layer_norm.weight" in self.pending else "group",
+                    conv_bias=fe + "0.conv.bias" in self.pending)
+            self.engine = SFCEngine(self.spec, self.device)
+            self.dirty = True
+        eng = self.engine
         if self.dirty:
             eng.load_encoder_state(self.pending, "wav2vec_model.model.")
             eng.load_head_state(self.pending, "seg_model.")
@@ -62,14 +73,16 @@ def _pretrained_encoder_state(name: str, spec: ModelSpec) -> dict:
     HFWav2Vec2.__init__, lib/models.py:334). Sources, in order: a local directory / HF cache via
     transformers (weights only, no compute), or seeded random init when W2VSEG_RANDOM_INIT=1."""
     if os.environ.get("W2VSEG_RANDOM_INIT", "0") == "1":
+        spec = dataclasses.replace(spec, feat_norm=os.environ.get("W2VSEG_FEAT_NORM", "layer"))
         sd = random_state_dict(spec, seed=int(os.environ.get("W2VSEG_SEED", "0")))
         return {k: v for k, v in sd.items() if k.startswith("wav2vec_model.model.")}
     from transformers import Wav2Vec2Model
 
     hf = Wav2Vec2Model.from_pretrained(name)
-    if getattr(hf.config, "feat_extract_norm", "layer") != "layer":
-        raise NotImplementedError("only feat_extract_norm='layer' encoders (XLS-R / wav2vec2-large-lv60) "
-                                  "are supported by the CUDA path")
+    if not getattr(hf.config, "do_stable_layer_norm", True):
+        raise NotImplementedError("post-LayerNorm encoders (do_stable_layer_norm=False: wav2vec2-base / -large-960h) "
+                                  "are not supported by the CUDA path; both feature-extractor variants "
+                                  "(feat_extract_norm 'layer' and 'group') are")
     return {"wav2vec_model.model." + k: v for k, v in hf.state_dict().items()}
 
 

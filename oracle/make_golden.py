@@ -39,8 +39,13 @@ def write_wav(path, x: torch.Tensor):
 
 
 def build_reference_model(ns, spec: synth.ModelSpec, seed: int):
+    from oracle import ref_shims
+
     finetune = spec.adapter_layers > 0
-    m = ns.models.SHAS("facebook/wav2vec2-xls-r-300m", spec.keep_layers, finetune,
+    name = "facebook/wav2vec2-xls-r-300m"
+    if spec.feat_norm == "group":
+        name = ref_shims.GROUP_NORM_NAME if spec.conv_bias else ref_shims.GROUP_NORM_NOBIAS_NAME
+    m = ns.models.SHAS(name, spec.keep_layers, finetune,
                        spec.adapter_layers if finetune else 99, False, False, True,
                        spec.head_layers, spec.head_heads, 0.1)
     sd = synth.random_state_dict(spec, seed)
@@ -76,7 +81,8 @@ def gold_batch(ns, name, spec, seed, lens, audio_seed):
     frames = sorted(set(list(range(0, hidden.shape[1], 9)) + list(range(max(0, hidden.shape[1] - 4), hidden.shape[1]))))
     np.savez_compressed(
         GOLD / f"{name}.npz",
-        spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads]),
+        spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads,
+                       int(spec.feat_norm == "group"), int(spec.conv_bias)]),
         seed=seed, audio_seed=audio_seed, lens=np.array(lens),
         hidden_frames=np.array(frames), hidden=hidden[:, frames, :].numpy().astype(np.float32),
         hidden_T=hidden.shape[1],
@@ -388,6 +394,10 @@ def main():
         # TINY (2 layers, last one with adapter): ragged batch incl. a window whose out_mask is one
         # frame longer than the encoder mask and a short one
         "tiny_batch": lambda: gold_batch(ns, "tiny_batch", synth.TINY, 0, [64000, 113234, 48000], 10),
+        # GroupNorm feature extractor (HF feat_extract_norm="group"): ragged batches with / without conv bias;
+        # the GroupNorm statistics run over the PADDED row, so the padding of the batch matters
+        "tiny_gn_batch": lambda: gold_batch(ns, "tiny_gn_batch", synth.TINY_GN, 0, [64000, 113234, 48000], 70),
+        "tiny_gn_nobias_batch": lambda: gold_batch(ns, "tiny_gn_nobias_batch", synth.TINY_GN_NOBIAS, 0, [160000, 90001], 71),
         # BASELINE.json configs[0]: middle (0/16), frozen encoder, single 20 s window
         "middle_window": lambda: gold_batch(ns, "middle_window", synth.MIDDLE, 0, [320000], 20),
         # middle+half (8/16): adapters in layers 8..15, ragged pair

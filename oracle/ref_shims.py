@@ -29,7 +29,11 @@ def reference_available() -> bool:
     return (REFERENCE_ROOT / "lib" / "models.py").exists()
 
 
-def xlsr_config():
+GROUP_NORM_NAME = "synthetic/xls-r-300m-group-norm"          # feat_extract_norm="group", conv_bias=True
+GROUP_NORM_NOBIAS_NAME = "synthetic/xls-r-300m-group-norm-nobias"
+
+
+def xlsr_config(feat_extract_norm="layer", conv_bias=True):
     from transformers import Wav2Vec2Config
 
     return Wav2Vec2Config(
@@ -39,9 +43,9 @@ def xlsr_config():
         intermediate_size=4096,
         hidden_act="gelu",
         layer_norm_eps=1e-5,
-        feat_extract_norm="layer",
+        feat_extract_norm=feat_extract_norm,
         feat_extract_activation="gelu",
-        conv_bias=True,
+        conv_bias=conv_bias,
         conv_dim=(512,) * 7,
         conv_kernel=(10, 3, 3, 3, 3, 2, 2),
         conv_stride=(5, 2, 2, 2, 2, 2, 2),
@@ -84,8 +88,14 @@ def install():
 
         from transformers import Wav2Vec2Model, Wav2Vec2Processor
 
-        cfg = xlsr_config()
-        Wav2Vec2Model.from_pretrained = classmethod(lambda cls, name, *a, **k: cls(cfg))
+        def _cfg(name):   # the architecture is chosen by the (fake) model name SHAS passes through
+            if name == GROUP_NORM_NAME:
+                return xlsr_config("group", True)
+            if name == GROUP_NORM_NOBIAS_NAME:
+                return xlsr_config("group", False)
+            return xlsr_config()
+
+        Wav2Vec2Model.from_pretrained = classmethod(lambda cls, name, *a, **k: cls(_cfg(name)))
         Wav2Vec2Processor.from_pretrained = classmethod(
             lambda cls, *a, **k: types.SimpleNamespace(
                 tokenizer=types.SimpleNamespace(get_vocab=lambda: {})

@@ -67,12 +67,23 @@ def normalize_rows(audio: torch.Tensor, included) -> torch.Tensor:
 
 
 def feature_extractor(sd, x: torch.Tensor) -> torch.Tensor:
-    """7 x [Conv1d -> LayerNorm over channels -> GELU] (HF:275-299, 382-419). x [B, L] -> [B, T, 512]"""
+    """x [B, L] -> [B, T, 512]. feat_extract_norm "layer": 7 x [Conv1d -> LayerNorm over channels -> GELU]
+    (HF:275-299, 382-419). "group" (recognised by the absence of conv_layers.1.layer_norm): conv 0 ->
+    GroupNorm(num_groups = channels, i.e. per channel over TIME of the padded row) -> GELU, conv 1..6 -> GELU
+    (HF:302-323, 249-272, 388-391). Conv biases are optional (config.conv_bias)."""
     dtype = x.dtype
     h = x[:, None, :]
+    group = f"{W2V}feature_extractor.conv_layers.1.layer_norm.weight" not in sd
     for l, s in enumerate(CONV_STRIDE):
         p = f"{W2V}feature_extractor.conv_layers.{l}."
-        h = F.conv1d(h, _get(sd, p + "conv.weight", dtype), _get(sd, p + "conv.bias", dtype), stride=s)
+        bias = _get(sd, p + "conv.bias", dtype) if p + "conv.bias" in sd else None
+        h = F.conv1d(h, _get(sd, p + "conv.weight", dtype), bias, stride=s)
+        if group:
+            if l == 0:
+                h = F.group_norm(h, h.shape[1], _get(sd, p + "layer_norm.weight", dtype),
+                                 _get(sd, p + "layer_norm.bias", dtype), 1e-5)
+            h = F.gelu(h)
+            continue
         h = h.transpose(1, 2)
         h = F.layer_norm(h, (h.shape[-1],), _get(sd, p + "layer_norm.weight", dtype),
                          _get(sd, p + "layer_norm.bias", dtype), 1e-5)

@@ -14,7 +14,7 @@ from wav2vecsegmenter_b200 import synth
 from util import load_gold, make_batch, spec_of
 
 
-@pytest.mark.parametrize("name", ["tiny_batch", "middle_window"])
+@pytest.mark.parametrize("name", ["tiny_batch", "middle_window", "tiny_gn_batch", "tiny_gn_nobias_batch"])
 def test_forward_oracle_matches_reference(name):
     g = load_gold(name)
     spec = spec_of(g)

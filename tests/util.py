@@ -14,8 +14,11 @@ def load_gold(name):
 
 
 def spec_of(g):
-    k, a, hl, hh = [int(x) for x in g["spec"]]
-    return synth.ModelSpec(keep_layers=k, adapter_layers=a, head_layers=hl, head_heads=hh)
+    k, a, hl, hh = [int(x) for x in g["spec"][:4]]
+    extra = {}
+    if len(g["spec"]) > 4:
+        extra = {"feat_norm": "group" if int(g["spec"][4]) else "layer", "conv_bias": bool(int(g["spec"][5]))}
+    return synth.ModelSpec(keep_layers=k, adapter_layers=a, head_layers=hl, head_heads=hh, **extra)
 
 
 def make_batch(lens, audio_seed):

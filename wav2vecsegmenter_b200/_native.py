@@ -14,6 +14,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("W2VSEG_LIB") or Path(__file__).resolve().parent / "csrc" / "libw2vseg.so")
 
 _lib = None
+ABI_VERSION = 2   # W2VSEG_ABI_VERSION of include/w2vseg.h this binding was written against
 
 
 class W2VSegError(RuntimeError):
@@ -38,6 +39,8 @@ class Config(C.Structure):
         ("head_heads", C.c_int32),
         ("head_ffn", C.c_int32),
         ("ln_eps", C.c_float),
+        ("feat_group_norm", C.c_int32),
+        ("conv_bias", C.c_int32),
     ]
 
 
@@ -96,7 +99,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.w2vseg_abi_version() != 1:
+    if lib.w2vseg_abi_version() != ABI_VERSION:
         raise W2VSegError("libw2vseg.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

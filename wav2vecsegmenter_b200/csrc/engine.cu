@@ -78,6 +78,7 @@ struct Workspace {
   float2* stats; int32_t* enc_len; int32_t* included; double2* stat_partial;
   bf16* conv[7];
   bf16* feat; float* h; bf16* zpad; bf16* xn; bf16* qkv; bf16* ctx; bf16* mid;
+  float* gn_scratch;   // GroupNorm extractor only: per-block channel sums + per-window folded taps
   size_t bytes;
 };
 
@@ -170,14 +171,26 @@ void build_layout(w2vseg_handle* h) {
   }
   for (int l = 0; l < 7; ++l) {
     const std::string p = "fe.conv" + std::to_string(l);
-    if (l == 0) add_vec(h, p + ".bias", &h->conv_b[l], CD);   // folded into the fp16 pack of conv0_tc
-    else add_bias(h, p + ".bias", &h->conv_b[l], CD);
-    add_ln(h, p + ".ln", &h->conv_ln[l], CD);
+    const bool gn = c.feat_group_norm != 0;
+    if (!c.conv_bias) {                  // no conv biases in this architecture: a zero vector (arena is zero-filled)
+      if (l == 0) h->conv_b[l] = h->alloc<float>(CD);
+      else add_bias(h, "", &h->conv_b[l], CD);
+    } else if (l == 0) {
+      add_vec(h, p + ".bias", &h->conv_b[l], CD);   // folded into the fp16 pack of conv0_tc / the GroupNorm taps
+    } else {
+      add_bias(h, p + ".bias", &h->conv_b[l], CD);
+    }
+    if (!gn || l == 0) add_ln(h, p + ".ln", &h->conv_ln[l], CD);   // "group": GroupNorm affine after conv 0 only
     if (l > 0) {
       h->conv_w[l] = h->alloc<bf16>((size_t)CD * CD * kConvK[l]);
       h->conv_x[l] = h->alloc<float>((size_t)CD * kConvK[l]);
       Slot s; s.kind = SLOT_CONV; s.numel = (int64_t)CD * CD * kConvK[l]; s.bdst = h->conv_w[l];
-      s.O = CD; s.I = CD; s.J = kConvK[l]; s.c_bias = h->conv_b[l]; s.c_x = h->conv_x[l];
+      s.O = CD; s.I = CD; s.J = kConvK[l];
+      // Bias correction needs E[x] to carry over from the calibration signal to the data. After a per-frame
+      // LayerNorm it does; in the GroupNorm variant the conv inputs are only normalised per channel over TIME,
+      // their mean follows the signal's loudness profile, and a calibrated correction does more harm than good
+      // (measured: hidden-state error 0.7 % -> 2.4 %): conv layers are left uncorrected there.
+      if (!gn) { s.c_bias = h->conv_b[l]; s.c_x = h->conv_x[l]; }
       h->slots[p + ".weight"] = s;
     }
   }
@@ -302,6 +315,9 @@ Workspace carve(const w2vseg_handle* h, uint8_t* base, int B, int R) {
   w.qkv = reinterpret_cast<bf16*>(take(M * 3 * D * sizeof(bf16)));
   w.ctx = reinterpret_cast<bf16*>(take(M * D * sizeof(bf16)));
   w.mid = reinterpret_cast<bf16*>(take(M * (size_t)h->F1max * sizeof(bf16)));
+  w.gn_scratch = h->cfg.feat_group_norm
+                     ? reinterpret_cast<float*>(take(conv0_gn_scratch_floats(B, R << 6) * sizeof(float)))
+                     : nullptr;
   w.bytes = align_up(off, 1024);
   return w;
 }
@@ -349,7 +365,7 @@ int check_ready(const w2vseg_handle* h) {
 // calib: additionally record the mean input row of every GEMM (w2vseg_calibrate)
 int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_t audio_stride,
                 const int32_t* sample_len, const int32_t* norm_len, int B, int R, cudaStream_t st,
-                bool calib = false) {
+                bool calib = false, int64_t l_max_samples = 0) {
   const w2vseg_config& c = h->cfg;
   const int D = h->D, CD = c.conv_dim;
   const int64_t M = (int64_t)B * R;
@@ -359,7 +375,12 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
 
   // conv feature extractor (HF:382-419). Layer l activations: channels-last bf16 [B*R*2^(6-l), 512].
   const int R0 = R << 6;
-  if (h->conv0_cuda_cores)
+  const bool gn = c.feat_group_norm != 0;
+  if (gn)   // GroupNorm over time: statistics over the padded row of the reference batch (norm_len)
+    W2V_TRY(conv0_gn_gelu_launch(audio, audio_stride, sample_len, norm_len, (int)l_max_samples, w.stats, h->conv0_wt,
+                                 c.conv_bias ? h->conv_b[0] : nullptr, h->conv_ln[0].g, h->conv_ln[0].b, c.ln_eps,
+                                 w.gn_scratch, w.conv[0], B, R0, st));
+  else if (h->conv0_cuda_cores)
     W2V_TRY(conv0_ln_gelu_launch(audio, audio_stride, sample_len, w.stats, h->conv0_wt, h->conv_b[0],
                                  h->conv_ln[0].g, h->conv_ln[0].b, c.ln_eps, w.conv[0], B, R0, st));
   else
@@ -372,12 +393,15 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
     GemmProblem g = linear(w.conv[l - 1], rows_out, kConvK[l] * CD, h->conv_w[l], CD, h->conv_b[l]);
     g.a_row_stride = 2 * CD;  // stride-2 conv: consecutive output frames start 2 input rows apart
     g.out = w.conv[l]; g.ld_out = CD;
+    if (gn) { g.act_lo = ACT_GELU; g.act_hi = ACT_GELU; }   // no norm after conv 1..6: GELU in the GEMM epilogue
     if (calib) W2V_TRY(colmean_launch(w.conv[l - 1], 2 * CD, kConvK[l] * CD, 1, (int)rows_out, 0, h->conv_x[l], h->calib_scratch, kCalibScratch, st));
     prof_tag(kConvK[l] == 3 ? "gemm.conv_k3" : "gemm.conv_k2");
     W2V_TRY(gemm_tc2_launch(g, st));
-    prof_tag("ln_gelu.conv");
-    W2V_TRY(layernorm_launch(w.conv[l], false, rows_out, CD, h->conv_ln[l].g, h->conv_ln[l].b,
-                             c.ln_eps, /*gelu*/ 1, w.conv[l], st));
+    if (!gn) {
+      prof_tag("ln_gelu.conv");
+      W2V_TRY(layernorm_launch(w.conv[l], false, rows_out, CD, h->conv_ln[l].g, h->conv_ln[l].b,
+                               c.ln_eps, /*gelu*/ 1, w.conv[l], st));
+    }
   }
 
   // feature projection (HF:429-434) with the frame mask fused (HF:753-756)
@@ -529,7 +553,8 @@ int32_t w2vseg_create(const w2vseg_config* cfg, w2vseg_handle** out) {
   if (cfg->head_layers > 0 && cfg->head_ffn > h->F1max) h->F1max = cfg->head_ffn;
   build_layout(h);  // sizing pass
   h->arena_bytes = h->arena_used + 4096;
-  if (cudaMalloc(&h->arena, h->arena_bytes) != cudaSuccess) {
+  if (cudaMalloc(&h->arena, h->arena_bytes) != cudaSuccess ||
+      cudaMemset(h->arena, 0, h->arena_bytes) != cudaSuccess) {
     set_error("create: cudaMalloc of %zu weight bytes failed", h->arena_bytes);
     delete h;
     return W2VSEG_ERR_CUDA;
@@ -600,9 +625,10 @@ int32_t w2vseg_finalize_weights(w2vseg_handle* h, void* stream) {
     W2V_TRY(weightnorm_scale_launch(h->pos_v, h->pos_g, h->D * gc, c.pos_kernel, h->pos_scale, st));
     W2V_TRY(pack_conv_launch(h->pos_v, h->D, gc, c.pos_kernel, h->pos_scale, h->pos_w, st));
   }
-  // conv layer 0: centred, gamma-scaled fp16 taps + Cholesky factor of the channel Gram matrix
-  W2V_TRY(conv0_tc_pack_launch(h->conv0_wt, 1, c.conv_dim, h->conv_b[0], h->conv_ln[0].g,
-                               h->conv_ln[0].b, h->conv0_pack, st));
+  // conv layer 0 (LayerNorm variant): centred, gamma-scaled fp16 taps + Cholesky factor of the channel Gram matrix
+  if (!c.feat_group_norm)
+    W2V_TRY(conv0_tc_pack_launch(h->conv0_wt, 1, c.conv_dim, h->conv_b[0], h->conv_ln[0].g,
+                                 h->conv_ln[0].b, h->conv0_pack, st));
   for (auto& L : h->enc) {
     if (L.adapter) W2V_TRY(axpby_launch(L.b2_raw, 1.f, L.bu_raw, c.adapter_scale, L.b2, h->D, st));
     else W2V_TRY(axpby_launch(L.b2_raw, 1.f, nullptr, 0.f, L.b2, h->D, st));
@@ -647,7 +673,7 @@ int32_t w2vseg_calibrate(w2vseg_handle* h, const float* audio, int64_t audio_str
   const int R = w2vseg_frame_stride(l_max);
   Workspace w;
   W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
-  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, /*calib*/ true));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, /*calib*/ true, l_max));
   W2V_TRY(run_head(h, w, w.h, B, R, out_len, nullptr, nullptr, st, 0, 0, -1, /*calib*/ true));
   h->calibrated = true;
   // the positional conv keeps its fp32 weight-norm factors in the handle: correct its bias right here
@@ -698,7 +724,7 @@ int32_t w2vseg_encode(w2vseg_handle* h, const float* audio, int64_t audio_stride
   const int R = w2vseg_frame_stride(l_max);
   Workspace w;
   W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
-  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, false, l_max));
   W2V_CHECK_CUDA(cudaMemcpyAsync(hidden_out, w.h, (size_t)B * R * h->D * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st));
   if (enc_len_out != nullptr)
@@ -738,7 +764,7 @@ int32_t w2vseg_sfc_forward(w2vseg_handle* h, const float* audio, int64_t audio_s
   const int R = w2vseg_frame_stride(l_max);
   Workspace w;
   W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
-  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, false, l_max));
   W2V_TRY(run_head(h, w, w.h, B, R, out_len, logits_out, probs_out, st));
   if (included_out != nullptr)
     W2V_CHECK_CUDA(cudaMemcpyAsync(included_out, w.included, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
@@ -762,7 +788,7 @@ int32_t w2vseg_sfc_forward_rows(w2vseg_handle* h, const float* audio, int64_t au
               (long long)row_stride, row_cols, flag_col, R);
   Workspace w;
   W2V_TRY(check_ws(h, workspace, workspace_bytes, B, R, &w));
-  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st));
+  W2V_TRY(run_encoder(h, w, audio, audio_stride, sample_len, norm_len, B, R, st, false, l_max));
   W2V_TRY(run_head(h, w, w.h, B, R, out_len, nullptr, rows_out, st, row_stride, row_cols, flag_col));
   return 0;
 }

@@ -386,6 +386,189 @@ gather_rows_kernel(const float* __restrict__ src, long long batch_stride, int T,
 
 // =============================================================================================
 // head: LayerNorm(C) -> dot(w) + b -> sigmoid -> mask      (one warp per frame, C = 1024)
+
+// =============================================================================================
+// GroupNorm feature extractor (HF feat_extract_norm = "group", HF:302-323): conv layer 0 is followed by
+// GroupNorm(num_groups = 512 = channels), i.e. every channel of every window is normalised over TIME — over the
+// frames of the PADDED row of the reference batch (CollateFn pads, normalises, and the conv stack sees all of it).
+// Three passes: (1) per-block partial sums of y and y^2 per channel, (2) per-window finalisation in fp64 that
+// folds mean / rstd / gamma / beta into a per-window copy of the 10 taps and a constant per channel, (3) the conv
+// with those taps + GELU. Sample i of window b as the reference's conv sees it:
+//   i < len: (x - mean) * rstd | len <= i < norm_len: (0 - mean) * rstd (normalised padding) |
+//   norm_len == 0 (audio already normalised by the caller): the buffer content up to l_max.
+constexpr int GN_PART_FLOATS = 8 * 2 * 512;   // per-warp partial sums of a block (dynamic shared memory)
+
+__device__ __forceinline__ float gn_sample(const float* __restrict__ x, long long i, int len, int nl, int l_max,
+                                           float2 st) {
+  if (i < len) return (x[i] - st.x) * st.y;
+  if (nl > 0) return i < nl ? (0.f - st.x) * st.y : 0.f;
+  return i < l_max ? x[i] : 0.f;
+}
+
+__global__ void __launch_bounds__(C0_THREADS, 2)
+conv0_gn_stats_kernel(const float* __restrict__ audio, long long audio_stride, const int* __restrict__ sample_len,
+                      const int* __restrict__ norm_len, int l_max, const float2* __restrict__ stats,
+                      const float* __restrict__ w_t, const float* __restrict__ bias, float* __restrict__ partial,
+                      int n_blk) {
+  extern __shared__ float4 gn_smem[];
+  float4* w_s = gn_smem;                                   // [10][128]
+  float4* b_s = gn_smem + 10 * 128;                        // [128]
+  float* x_s = reinterpret_cast<float*>(gn_smem + 11 * 128);   // [C0_ROWS * 5 + 8]
+  float* part = x_s + C0_ROWS * 5 + 8;                     // [8 warps][2][512]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0_ROWS;
+  const int len = sample_len[b], nl = norm_len[b];
+  const int n_pad = nl > 0 ? nl : l_max;
+  const int Tn = n_pad >= 10 ? (n_pad - 10) / 5 + 1 : 0;   // conv-0 frames of the padded row
+  const float2 st = stats[b];
+  const float* x = audio + (long long)b * audio_stride;
+  for (int i = threadIdx.x; i < 10 * 128; i += C0_THREADS) w_s[i] = reinterpret_cast<const float4*>(w_t)[i];
+  for (int i = threadIdx.x; i < 128; i += C0_THREADS)
+    b_s[i] = bias != nullptr ? reinterpret_cast<const float4*>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < C0_ROWS * 5 + 5; i += C0_THREADS)
+    x_s[i] = gn_sample(x, (long long)t0 * 5 + i, len, nl, l_max, st);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s1[16], s2[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  for (int tl = warp * C0_F; tl < C0_ROWS; tl += (C0_THREADS / 32) * C0_F) {
+    if (t0 + tl >= Tn) break;
+    float acc[C0_F][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bi = b_s[q * 32 + lane];
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f) {
+        acc[f][4 * q + 0] = bi.x; acc[f][4 * q + 1] = bi.y; acc[f][4 * q + 2] = bi.z; acc[f][4 * q + 3] = bi.w;
+      }
+    }
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+      float xv[C0_F];
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f) xv[f] = x_s[(tl + f) * 5 + j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = w_s[j * 128 + q * 32 + lane];
+#pragma unroll
+        for (int f = 0; f < C0_F; ++f) {
+          acc[f][4 * q + 0] = fmaf(xv[f], w.x, acc[f][4 * q + 0]);
+          acc[f][4 * q + 1] = fmaf(xv[f], w.y, acc[f][4 * q + 1]);
+          acc[f][4 * q + 2] = fmaf(xv[f], w.z, acc[f][4 * q + 2]);
+          acc[f][4 * q + 3] = fmaf(xv[f], w.w, acc[f][4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < C0_F; ++f)
+      if (t0 + tl + f < Tn) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { s1[c] += acc[f][c]; s2[c] = fmaf(acc[f][c], acc[f][c], s2[c]); }
+      }
+  }
+  // channel of (q, lane, e) = (q*32 + lane)*4 + e, as in the float4 weight rows
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = (q * 32 + lane) * 4 + e;
+      part[(warp * 2 + 0) * 512 + ch] = s1[4 * q + e];
+      part[(warp * 2 + 1) * 512 + ch] = s2[4 * q + e];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 512; i += C0_THREADS) {   // fixed summation order: deterministic
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += part[w * 1024 + i];
+    partial[((long long)b * n_blk + blockIdx.x) * 1024 + i] = a;
+  }
+}
+
+// per window: fp64 totals -> mean / rstd per channel -> taps and constant with the normalisation folded in
+//   wg[b][j][c] = w[j][c] * rstd * gamma[c],  cg[b][c] = (bias[c] - mean) * rstd * gamma[c] + beta[c]
+__global__ void __launch_bounds__(512)
+conv0_gn_finalize_kernel(const float* __restrict__ partial, int n_blk, const int* __restrict__ norm_len, int l_max,
+                         const float* __restrict__ w_t, const float* __restrict__ bias,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         float* __restrict__ wg) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const int nl = norm_len[b];
+  const int n_pad = nl > 0 ? nl : l_max;
+  const int Tn = n_pad >= 10 ? (n_pad - 10) / 5 + 1 : 0;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < n_blk; ++k) {
+    s1 += (double)partial[((long long)b * n_blk + k) * 1024 + c];
+    s2 += (double)partial[((long long)b * n_blk + k) * 1024 + 512 + c];
+  }
+  const double mean = Tn > 0 ? s1 / Tn : 0.0;
+  const double var = Tn > 0 ? fmax(s2 / Tn - mean * mean, 0.0) : 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma[c] * rstd;
+  float* o = wg + (long long)b * 11 * 512;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) o[j * 512 + c] = w_t[j * 512 + c] * g;
+  o[10 * 512 + c] = ((bias != nullptr ? bias[c] : 0.f) - (float)mean) * g + beta[c];
+}
+
+__global__ void __launch_bounds__(C0_THREADS, 2)
+conv0_gn_gelu_kernel(const float* __restrict__ audio, long long audio_stride, const int* __restrict__ sample_len,
+                     const int* __restrict__ norm_len, int l_max, const float2* __restrict__ stats,
+                     const float* __restrict__ wg, __nv_bfloat16* __restrict__ out, int R0) {
+  __shared__ float4 w_s[11 * 128];
+  __shared__ float x_s[C0_ROWS * 5 + 8];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0_ROWS;
+  const int len = sample_len[b], nl = norm_len[b];
+  const float2 st = stats[b];
+  const float* x = audio + (long long)b * audio_stride;
+  const float4* wsrc = reinterpret_cast<const float4*>(wg + (long long)b * 11 * 512);
+  for (int i = threadIdx.x; i < 11 * 128; i += C0_THREADS) w_s[i] = wsrc[i];
+  for (int i = threadIdx.x; i < C0_ROWS * 5 + 5; i += C0_THREADS)
+    x_s[i] = gn_sample(x, (long long)t0 * 5 + i, len, nl, l_max, st);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int tl = warp * C0_F; tl < C0_ROWS; tl += (C0_THREADS / 32) * C0_F) {
+    if (t0 + tl >= R0) break;
+    float acc[C0_F][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bi = w_s[10 * 128 + q * 32 + lane];
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f) {
+        acc[f][4 * q + 0] = bi.x; acc[f][4 * q + 1] = bi.y; acc[f][4 * q + 2] = bi.z; acc[f][4 * q + 3] = bi.w;
+      }
+    }
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+      float xv[C0_F];
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f) xv[f] = x_s[(tl + f) * 5 + j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = w_s[j * 128 + q * 32 + lane];
+#pragma unroll
+        for (int f = 0; f < C0_F; ++f) {
+          acc[f][4 * q + 0] = fmaf(xv[f], w.x, acc[f][4 * q + 0]);
+          acc[f][4 * q + 1] = fmaf(xv[f], w.y, acc[f][4 * q + 1]);
+          acc[f][4 * q + 2] = fmaf(xv[f], w.z, acc[f][4 * q + 2]);
+          acc[f][4 * q + 3] = fmaf(xv[f], w.w, acc[f][4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int f = 0; f < C0_F; ++f)
+        if (t0 + tl + f < R0) {
+          uint2 u;
+          u.x = pack_bf16x2(gelu_erf(acc[f][4 * q + 0]), gelu_erf(acc[f][4 * q + 1]));
+          u.y = pack_bf16x2(gelu_erf(acc[f][4 * q + 2]), gelu_erf(acc[f][4 * q + 3]));
+          reinterpret_cast<uint2*>(out + ((long long)b * R0 + t0 + tl + f) * 512)[q * 32 + lane] = u;
+        }
+  }
+}
+
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 head_final_kernel(const float* __restrict__ y, long long rows, int R,
@@ -676,6 +859,41 @@ int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t
   conv0_ln_gelu_kernel<<<grid, C0_THREADS, 0, s>>>(audio, audio_stride, sample_len, stats, w_t,
                                                    bias, gamma, beta, eps, out, R0);
   W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+
+size_t conv0_gn_scratch_floats(int B, int R0) {
+  const size_t n_blk = (size_t)(R0 + C0_ROWS - 1) / C0_ROWS;
+  return (size_t)B * n_blk * 1024 + (size_t)B * 11 * 512;
+}
+
+int conv0_gn_gelu_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                         const int32_t* norm_len, int l_max, const float2* stats, const float* w_t,
+                         const float* bias, const float* gamma, const float* beta, float eps,
+                         float* scratch, __nv_bfloat16* out, int B, int R0, cudaStream_t s) {
+  if (B <= 0 || R0 <= 0) return 0;
+  const int n_blk = (R0 + C0_ROWS - 1) / C0_ROWS;
+  float* partial = scratch;
+  float* wg = scratch + (size_t)B * n_blk * 1024;
+  const size_t smem = sizeof(float4) * 11 * 128 + sizeof(float) * (C0_ROWS * 5 + 8 + GN_PART_FLOATS);
+  W2V_ONCE_BEGIN
+  W2V_CHECK_CUDA(cudaFuncSetAttribute(conv0_gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  W2V_ONCE_END
+  dim3 grid(n_blk, B);
+  {
+    ProfScope ps(s, "conv0_gn_stats");
+    conv0_gn_stats_kernel<<<grid, C0_THREADS, smem, s>>>(audio, audio_stride, sample_len, norm_len, l_max, stats, w_t,
+                                                          bias, partial, n_blk);
+    W2V_CHECK_LAUNCH();
+  }
+  conv0_gn_finalize_kernel<<<B, 512, 0, s>>>(partial, n_blk, norm_len, l_max, w_t, bias, gamma, beta, eps, wg);
+  W2V_CHECK_LAUNCH();
+  {
+    ProfScope ps(s, "conv0_gn_gelu");
+    conv0_gn_gelu_kernel<<<grid, C0_THREADS, 0, s>>>(audio, audio_stride, sample_len, norm_len, l_max, stats, wg, out, R0);
+    W2V_CHECK_LAUNCH();
+  }
   return 0;
 }
 

@@ -18,6 +18,15 @@ int conv0_ln_gelu_launch(const float* audio, int64_t audio_stride, const int32_t
                          const float* gamma, const float* beta, float eps, __nv_bfloat16* out,
                          int B, int R0, cudaStream_t s);
 
+// GroupNorm variant of layer 0 (HF feat_extract_norm="group", HF:302-323): conv -> GroupNorm(512 groups: per
+// channel over the frames of the padded row, norm_len[b] samples, or l_max if norm_len[b] == 0) -> GELU.
+// scratch: conv0_gn_scratch_floats(B, R0) floats. bias may be null (config.conv_bias = False).
+size_t conv0_gn_scratch_floats(int B, int R0);
+int conv0_gn_gelu_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,
+                         const int32_t* norm_len, int l_max, const float2* stats, const float* w_t,
+                         const float* bias, const float* gamma, const float* beta, float eps,
+                         float* scratch, __nv_bfloat16* out, int B, int R0, cudaStream_t s);
+
 // same layer on the tensor cores (conv0_tc.cu): LayerNorm folded into ONE K=16 fp16 tcgen05.mma per
 // 128-frame x 256-channel tile, GELU in the epilogue. `pack` = conv0_tc_pack_bytes() device bytes
 // filled once per weight set by conv0_tc_pack_launch (w element (c,k) at w[c*sc + k*sk]).

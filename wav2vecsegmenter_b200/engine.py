@@ -68,6 +68,7 @@ class SFCEngine:
             adapter_scale=spec.adapter_scale, conv_dim=spec.conv_dim, pos_kernel=spec.pos_kernel,
             pos_groups=spec.pos_groups, head_layers=spec.head_layers, head_heads=spec.head_heads,
             head_ffn=spec.head_ffn, ln_eps=spec.ln_eps,
+            feat_group_norm=int(spec.feat_norm == "group"), conv_bias=int(spec.conv_bias),
         )
         h = nat.C.c_void_p()
         nat.check(self.lib.w2vseg_create(nat.C.byref(cfg), nat.C.byref(h)), "w2vseg_create")

@@ -35,6 +35,10 @@ class ModelSpec:
     head_heads: int = 8            # n_transformer_enc_heads
     head_ffn: int = 2048
     ln_eps: float = 1e-5
+    # feature-extractor variant (HF config.feat_extract_norm): "layer" = LayerNorm + GELU after every conv
+    # (XLS-R, HF:275-299), "group" = GroupNorm(512 groups) after conv 0 only (HF:302-323, 388-391)
+    feat_norm: str = "layer"
+    conv_bias: bool = True
 
     @staticmethod
     def from_shas_kwargs(wav2vec_keep_layers, finetune_wav2vec, wav2vec_ft_layers, ffn_adapter,
@@ -55,6 +59,8 @@ LARGE_ALL = ModelSpec(keep_layers=24, adapter_layers=24)      # large (24/24) + 
 MIDDLE = ModelSpec(keep_layers=16, adapter_layers=0)          # middle (0/16), frozen encoder
 MIDDLE_HALF = ModelSpec(keep_layers=16, adapter_layers=8)     # middle+half (8/16)
 TINY = ModelSpec(keep_layers=2, adapter_layers=1)             # test-sized
+TINY_GN = ModelSpec(keep_layers=2, adapter_layers=1, feat_norm="group")                     # GroupNorm extractor
+TINY_GN_NOBIAS = ModelSpec(keep_layers=2, adapter_layers=0, feat_norm="group", conv_bias=False)
 
 
 def random_state_dict(spec: ModelSpec, seed: int = 0, logit_std: float = 2.0) -> dict:
@@ -81,8 +87,10 @@ def random_state_dict(spec: ModelSpec, seed: int = 0, logit_std: float = 2.0) ->
     for l, k in enumerate(CONV_KERNEL):
         p = f"{w}feature_extractor.conv_layers.{l}"
         sd[p + ".conv.weight"] = randn(C, cin, k, std=1.4 / math.sqrt(cin * k))
-        sd[p + ".conv.bias"] = randn(C, std=0.05)
-        lnorm(sd, p + ".layer_norm", C)
+        if spec.conv_bias:
+            sd[p + ".conv.bias"] = randn(C, std=0.05)
+        if spec.feat_norm == "layer" or l == 0:     # "group": GroupNorm affine after conv 0 only (same key names)
+            lnorm(sd, p + ".layer_norm", C)
         cin = C
     lnorm(sd, w + "feature_projection.layer_norm", C)
     linear(sd, w + "feature_projection.projection", D, C)
