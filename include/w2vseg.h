@@ -197,6 +197,34 @@ int32_t w2vseg_sfc_forward_rows(w2vseg_handle* h, const float* audio, int64_t au
                                 int64_t row_stride, int32_t row_cols, int32_t flag_col,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- head-only training step (frozen encoder) --------------------------------------------------
+ * replaces, for the frozen-encoder setting (finetune_wav2vec=False: middle 0/16, large 0/24), the body of the
+ * reference's training loop train.py:381-480 after the encoder forward: SegmentationFrameClassifier forward
+ * (lib/models.py:307-319), BCEWithLogitsLoss(pos_weight, reduction none) -> masked -> .sum(dim=1).mean()
+ * (train.py:416-459, ma_window unset), and the backward pass down to every seg_model parameter. The encoder
+ * output comes from w2vseg_encode (no gradient flows into it). The optimiser stays with the caller: gradients are
+ * returned in fp32 in the PyTorch shape of each parameter, packed into one buffer:
+ *   w2vseg_head_grad_floats(h)                 total floats of the gradient buffer
+ *   w2vseg_head_grad_offset(h, name, &numel)   float offset of a parameter (canonical head.* names of
+ *                                              w2vseg_set_weight), -1 if unknown
+ * After the optimiser step the caller re-uploads the head parameters with w2vseg_set_weight("head....");
+ * that does not un-finalise the handle.
+ *   hidden      device fp32, window b frame t at hidden + b*batch_stride + t*hidden_dim (as w2vseg_head)
+ *   target      device fp32 [B, T] labels in [0, 1]
+ *   loss_out    device fp32 [1]; logits_out device fp32 [B, T] or NULL (0 where masked)
+ * Dropout (init_dropout and the layer's 0.1) is NOT applied: the step is the deterministic gradient of the
+ * eval-mode head, which is what the parity tests compare with torch.autograd.
+ * Arithmetic: bf16 GEMM operands (tcgen05, fp32 accumulate) for forward, dgrad and wgrad; attention backward
+ * recomputes S / P from the forward's row log-sum-exp (mma.sync, attention_bwd.cu); LayerNorm, GELU', loss and
+ * all reductions in fp32 with fixed summation orders (bit-reproducible). */
+int64_t w2vseg_head_grad_floats(const w2vseg_handle* h);
+int64_t w2vseg_head_grad_offset(const w2vseg_handle* h, const char* name, int64_t* numel_out);
+size_t w2vseg_head_train_workspace_bytes(const w2vseg_handle* h, int32_t B, int32_t T);
+int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t batch_stride, int32_t T,
+                               const int32_t* out_len, const float* target, float pos_weight, int32_t B,
+                               float* loss_out, float* logits_out, float* grads, size_t grads_floats,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- talk-level reductions (all device pointers) --------------------------------------------- */
 /* talk[0..n_frames) = NaN, then for each window row w: talk[start[w] .. start[w]+count[w]) =
  * (double) rows[w*row_stride .. +count[w]) ; count[w] < 0 writes zeros over -count[w] frames
@@ -263,6 +291,16 @@ int32_t w2vseg_attention(const void* qkv_bf16, int32_t B, int32_t R, int32_t hea
 int32_t w2vseg_attention_mma(const void* qkv_bf16, int32_t B, int32_t R, int32_t heads,
                              int32_t head_dim, const int32_t* kv_len, float scale, void* ctx_bf16,
                              void* stream);
+
+/* training forward of the head attention: w2vseg_attention_mma that also returns the per-row log-sum-exp
+ * (fp32 [B, heads, R], log2 domain) the backward re-exponentiates with */
+int32_t w2vseg_attention_train(const void* qkv_bf16, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                               const int32_t* kv_len, float scale, void* ctx_bf16, float* lse, void* stream);
+/* attention backward: dqkv bf16 [B*R, 3*heads*head_dim] (dQ | dK | dV) from dctx bf16 [B*R, heads*head_dim],
+ * the forward's qkv / ctx / lse; delta_scratch: fp32 [B, heads, R]. Rows >= kv_len[b] get zero dK / dV. */
+int32_t w2vseg_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* dctx_bf16, const float* lse,
+                             float* delta_scratch, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                             const int32_t* kv_len, float scale, void* dqkv_bf16, void* stream);
 
 #ifdef __cplusplus
 }

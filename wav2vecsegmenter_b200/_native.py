@@ -66,6 +66,12 @@ SIGNATURES = {
     "w2vseg_workspace_bytes": (_SZ, [_P, _I32, _I64]),
     "w2vseg_encode": (_I32, [_P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "w2vseg_head": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _SZ, _P]),
+    "w2vseg_attention_train": (_I32, [_P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P, _P]),
+    "w2vseg_attention_bwd": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),
+    "w2vseg_head_grad_floats": (_I64, [_P]),
+    "w2vseg_head_grad_offset": (_I64, [_P, C.c_char_p, C.POINTER(_I64)]),
+    "w2vseg_head_train_workspace_bytes": (_SZ, [_P, _I32, _I32]),
+    "w2vseg_head_train_step": (_I32, [_P, _P, _I64, _I32, _P, _P, C.c_float, _I32, _P, _P, _P, _SZ, _P, _SZ, _P]),
     "w2vseg_calibrate": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _SZ, _P]),
     "w2vseg_correct_bias": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
     "w2vseg_sfc_forward": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),

@@ -11,7 +11,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = CSRC / "libw2vseg.so"
-SOURCES = ["common.cu", "gemm_tc.cu", "gemm_tc2.cu", "posconv_tc.cu", "conv0_tc.cu", "kernels.cu", "attention.cu", "attention_tc.cu", "attention_tc64.cu", "engine.cu"]
+SOURCES = ["common.cu", "gemm_tc.cu", "gemm_tc2.cu", "posconv_tc.cu", "conv0_tc.cu", "kernels.cu", "attention.cu", "attention_bwd.cu", "attention_tc.cu", "attention_tc64.cu", "train_kernels.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

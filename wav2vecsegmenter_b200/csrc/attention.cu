@@ -13,70 +13,17 @@
 // [b*R, (b+1)*R); keys t >= kv_len[b] are masked. All R rows are produced as queries.
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "attention_mma.cuh"
 
 namespace w2v {
 
 namespace {
 
-constexpr int ATT_BQ = 64;     // query rows per CTA (16 per warp)
-constexpr int ATT_BKV = 64;    // keys per tile
-constexpr int ATT_THREADS = 128;
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0 => 16 zero bytes written
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                        uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1,
-                                              uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
-                                               uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// byte offset of 16-byte chunk `chunk` of row `row` in a [rows][DH] bf16 tile, XOR-swizzled so
-// that ldmatrix (8 rows x one chunk) and the row-contiguous cp.async fills are conflict-free
-template <int DH>
-__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
-  return (uint32_t)(row * (DH * 2) + ((chunk ^ (row & 7)) << 4));
-}
-
-template <int DH>
-__device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat16* gbase,
-                                          long long ld, int row0, int rows_valid) {
-  constexpr int CHUNKS = DH / 8;
-  for (int i = threadIdx.x; i < ATT_BKV * CHUNKS; i += ATT_THREADS) {
-    const int r = i / CHUNKS, c = i - r * CHUNKS;
-    const bool ok = (row0 + r) < rows_valid;
-    const __nv_bfloat16* src = gbase + (long long)(ok ? row0 + r : 0) * ld + c * 8;
-    cp_async16(smem_base + tile_off<DH>(r, c), src, ok);
-  }
-}
-
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
                  const int* __restrict__ kv_len, float scale_log2,
-                 __nv_bfloat16* __restrict__ ctx) {
+                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   constexpr int TILE_BYTES = ATT_BKV * DH * 2;
   const uint32_t sQ = smem_u32(att_smem);
@@ -224,6 +171,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
     inv[r] = l > 0.f ? 1.f / l : 0.f;
+    // training forward: row log-sum-exp in the log2 domain the backward re-exponentiates with,
+    // p = exp2(s * scale_log2 - lse); +inf for a row without any valid key (p = 0 everywhere)
+    if (lse != nullptr && (lane & 3) == 0) {
+      const int row = q0 + warp * 16 + (lane >> 2) + 8 * r;
+      if (row < R)
+        lse[((long long)b * heads + head) * R + row] = l > 0.f ? m_run[r] * scale_log2 + log2f(l) : INFINITY;
+    }
   }
   __syncwarp();
   const int r_lo = warp * 16 + (lane >> 2);
@@ -256,7 +210,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
 }  // namespace
 
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
-                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s) {
+                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s, float* lse) {
   if (B <= 0 || R <= 0) return 0;
   W2V_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim %d unsupported (64 / 128)",
               head_dim);
@@ -265,13 +219,13 @@ int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head
   const int smem = 5 * ATT_BKV * head_dim * 2;
   ProfScope ps(s, head_dim == 64 ? "attention_d64" : "attention_d128");
   if (head_dim == 64) {
-    attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
+    attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse);
   } else {
     W2V_ONCE_BEGIN
       W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     W2V_ONCE_END
-    attention_kernel<128><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx);
+    attention_kernel<128><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse);
   }
   W2V_CHECK_LAUNCH();
   return 0;

@@ -12,6 +12,7 @@
 
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace w2v;
 typedef __nv_bfloat16 bf16;
@@ -597,6 +598,16 @@ int32_t w2vseg_set_weight(w2vseg_handle* h, const char* name, const float* src, 
       break;
   }
   h->was_set[name] = true;
+  if (h->finalized && strncmp(name, "head.", 5) == 0) {
+    // training loop (w2vseg_head_train_step): head parameters are re-uploaded every optimiser step. The handle
+    // stays finalised; a re-uploaded head bias becomes the effective bias again (any bias correction of that
+    // vector is dropped, as after w2vseg_finalize_weights).
+    if (s.kind == SLOT_VEC)
+      for (const BiasPair& bp : h->bias_pairs)
+        if (bp.raw == s.fdst) W2V_TRY(axpby_launch(bp.raw, 1.f, nullptr, 0.f, bp.eff, bp.n, st));
+    h->corrected.erase(name);
+    return 0;
+  }
   h->finalized = false;
   h->calibrated = false;
   return 0;
@@ -889,6 +900,205 @@ int32_t w2vseg_attention_mma(const void* qkv, int32_t B, int32_t R, int32_t head
   W2V_REQUIRE(qkv && kv_len && ctx, "attention: null argument");
   return attention_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
                           (cudaStream_t)stream);
+}
+
+int32_t w2vseg_attention_train(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                               const int32_t* kv_len, float scale, void* ctx, float* lse, void* stream) {
+  W2V_REQUIRE(qkv && kv_len && ctx && lse, "attention_train: null argument");
+  return attention_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
+                          (cudaStream_t)stream, lse);
+}
+
+int32_t w2vseg_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse,
+                             float* delta_scratch, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
+                             const int32_t* kv_len, float scale, void* dqkv, void* stream) {
+  W2V_REQUIRE(qkv && ctx && dctx && lse && delta_scratch && kv_len && dqkv, "attention_bwd: null argument");
+  return attention_bwd_launch((const bf16*)qkv, (const bf16*)ctx, (const bf16*)dctx, lse, delta_scratch, B, R,
+                              heads, head_dim, kv_len, scale, (bf16*)dqkv, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---- head-only training step (frozen encoder) --------------------------------------------------------------
+namespace {
+
+struct GradSlot { const char* name; int64_t off; int64_t numel; };
+
+// gradient buffer layout: every seg_model parameter in its PyTorch shape, fp32, in this order
+std::vector<GradSlot> head_grad_layout(const w2vseg_handle* h) {
+  const int64_t D = h->D, F = h->cfg.head_ffn;
+  std::vector<GradSlot> v;
+  int64_t off = 0;
+  auto add = [&](const char* n, int64_t numel) { v.push_back({n, off, numel}); off += (numel + 63) / 64 * 64; };
+  if (h->cfg.head_layers > 0) {
+    add("head.in_proj.weight", 3 * D * D); add("head.in_proj.bias", 3 * D);
+    add("head.o.weight", D * D);           add("head.o.bias", D);
+    add("head.ff1.weight", F * D);         add("head.ff1.bias", F);
+    add("head.ff2.weight", D * F);         add("head.ff2.bias", D);
+    add("head.ln1.weight", D); add("head.ln1.bias", D);
+    add("head.ln2.weight", D); add("head.ln2.bias", D);
+  }
+  add("head.ln_f.weight", D); add("head.ln_f.bias", D);
+  add("head.out.weight", D);  add("head.out.bias", 1);
+  v.push_back({nullptr, off, 0});
+  return v;
+}
+
+struct TrainWs {
+  float *x0, *x1, *x2, *dx2, *dx1, *dlogit, *loss_rows, *lse, *delta, *red, *tmpA, *tmpS;
+  float2 *st0, *st1, *st2;
+  bf16 *u1, *u2, *qkv, *ctx, *z1, *m, *dx2b, *dm, *dz1, *du2, *dx1b, *dctx, *dqkv, *du1, *ta, *tb, *wt;
+  size_t bytes;
+};
+constexpr size_t kRedFloats = 64 * 2 * 4096;
+
+TrainWs carve_train(const w2vseg_handle* h, uint8_t* base, int B, int T) {
+  TrainWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    off = align_up(off, 1024);
+    uint8_t* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  const size_t M = (size_t)B * T, D = h->D, F = h->cfg.head_ffn, Mp = (M + 63) / 64 * 64;
+  const size_t heads = h->cfg.head_heads > 0 ? h->cfg.head_heads : 1;
+  auto f32 = [&](size_t n) { return reinterpret_cast<float*>(take(n * sizeof(float))); };
+  auto b16 = [&](size_t n) { return reinterpret_cast<bf16*>(take(n * sizeof(bf16))); };
+  w.x0 = f32(M * D); w.x1 = f32(M * D); w.x2 = f32(M * D); w.dx2 = f32(M * D); w.dx1 = f32(M * D);
+  w.dlogit = f32(M); w.loss_rows = f32(M); w.lse = f32(heads * M); w.delta = f32(heads * M);
+  w.red = f32(kRedFloats); w.tmpA = f32(4096); w.tmpS = f32(4096);
+  w.st0 = reinterpret_cast<float2*>(take(M * sizeof(float2)));
+  w.st1 = reinterpret_cast<float2*>(take(M * sizeof(float2)));
+  w.st2 = reinterpret_cast<float2*>(take(M * sizeof(float2)));
+  w.u1 = b16(M * D); w.u2 = b16(M * D); w.qkv = b16(M * 3 * D); w.ctx = b16(M * D);
+  w.z1 = b16(M * F); w.m = b16(M * F); w.dx2b = b16(M * D); w.dm = b16(M * F); w.dz1 = b16(M * F);
+  w.du2 = b16(M * D); w.dx1b = b16(M * D); w.dctx = b16(M * D); w.dqkv = b16(M * 3 * D); w.du1 = b16(M * D);
+  const size_t wide = std::max<size_t>(3 * D, F);
+  w.ta = b16(wide * Mp); w.tb = b16(wide * Mp);       // transposed activations [cols, Mp] for the wgrad GEMMs
+  w.wt = b16(std::max<size_t>(3 * D * D, D * F));    // transposed weight for the dgrad GEMMs
+  w.bytes = align_up(off, 1024);
+  return w;
+}
+
+// out[M, N] = A[M, K] * W[N, K]^T (+ bias); plain problem on the CTA-pair kernel
+int gemm_plain(const bf16* A, int64_t M, int K, const bf16* W, int N, const float* bias, void* out, int64_t ld_out,
+               bool out_f32, float* resid, const char* tag, cudaStream_t st) {
+  GemmProblem g = linear(A, M, K, W, N, bias);
+  g.out = out; g.ld_out = ld_out; g.out_f32 = out_f32 ? 1 : 0;
+  if (resid != nullptr) { g.resid = resid; g.ld_resid = ld_out; }
+  prof_tag(tag);
+  return gemm_tc2_launch(g, st);
+}
+// dW[N_w, K_w] (fp32) = dY[M, N_w]^T X[M, K_w]  as  A' = dY^T [N_w, Mp], W' = X^T [K_w, Mp]
+int wgrad(const bf16* dY, int64_t ld_dy, int N_w, const bf16* X, int64_t ld_x, int K_w, int64_t M, const TrainWs& w,
+          float* dW, cudaStream_t st) {
+  const int64_t Mp = (M + 63) / 64 * 64;
+  W2V_TRY(transpose_bf16_launch(dY, ld_dy, M, N_w, w.ta, Mp, st));
+  W2V_TRY(transpose_bf16_launch(X, ld_x, M, K_w, w.tb, Mp, st));
+  return gemm_plain(w.ta, N_w, (int)Mp, w.tb, K_w, nullptr, dW, K_w, true, nullptr, "train.wgrad", st);
+}
+// dX[M, K_w] (bf16) = dY[M, N_w] W[N_w, K_w]  as  W' = W^T [K_w, N_w]
+int dgrad(const bf16* dY, int64_t M, int N_w, const bf16* W, int64_t ld_w, int K_w, const TrainWs& w, bf16* dX,
+          cudaStream_t st) {
+  W2V_TRY(transpose_bf16_launch(W, ld_w, N_w, K_w, w.wt, N_w, st));
+  return gemm_plain(dY, M, N_w, w.wt, K_w, nullptr, dX, K_w, false, nullptr, "train.dgrad", st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t w2vseg_head_grad_floats(const w2vseg_handle* h) {
+  if (h == nullptr) return 0;
+  return head_grad_layout(h).back().off;
+}
+int64_t w2vseg_head_grad_offset(const w2vseg_handle* h, const char* name, int64_t* numel_out) {
+  if (h == nullptr || name == nullptr) return -1;
+  for (const GradSlot& g : head_grad_layout(h))
+    if (g.name != nullptr && strcmp(g.name, name) == 0) {
+      if (numel_out != nullptr) *numel_out = g.numel;
+      return g.off;
+    }
+  return -1;
+}
+size_t w2vseg_head_train_workspace_bytes(const w2vseg_handle* h, int32_t B, int32_t T) {
+  if (h == nullptr || B <= 0 || T <= 0) return 0;
+  return carve_train(h, nullptr, B, T).bytes + 1024;
+}
+
+int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t batch_stride, int32_t T,
+                               const int32_t* out_len, const float* target, float pos_weight, int32_t B,
+                               float* loss_out, float* logits_out, float* grads, size_t grads_floats,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  W2V_TRY(check_ready(h));
+  W2V_REQUIRE(hidden && out_len && target && loss_out && grads && workspace, "head_train_step: null argument");
+  W2V_REQUIRE(B > 0 && T > 0 && batch_stride >= (int64_t)T * h->D && batch_stride % 4 == 0,
+              "head_train_step: bad shape (B=%d, T=%d, batch_stride=%lld)", B, T, (long long)batch_stride);
+  W2V_REQUIRE(h->cfg.head_layers == 1, "head_train_step: needs the 1-layer transformer head");
+  const std::vector<GradSlot> lay = head_grad_layout(h);
+  W2V_REQUIRE(grads_floats >= (size_t)lay.back().off, "head_train_step: gradient buffer too small (%zu floats, %lld needed)",
+              grads_floats, (long long)lay.back().off);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const TrainWs w = carve_train(h, base, B, T);
+  W2V_REQUIRE(workspace_bytes >= w.bytes + (size_t)(base - reinterpret_cast<uint8_t*>(workspace)),
+              "head_train_step: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, w.bytes + 1024);
+  auto G = [&](const char* name) -> float* {
+    for (const GradSlot& g : lay)
+      if (g.name != nullptr && strcmp(g.name, name) == 0) return grads + g.off;
+    return nullptr;
+  };
+  const w2vseg_config& c = h->cfg;
+  const HeadW& H = h->head;
+  const int D = h->D, F = c.head_ffn, hd = D / c.head_heads;
+  const int64_t M = (int64_t)B * T;
+  const float scale = 1.0f / sqrtf((float)hd);
+
+  // ---------------- forward, keeping what the backward needs (dropout: not applied, see w2vseg.h)
+  W2V_TRY(gather_rows_launch(hidden, batch_stride, B, T, D, w.x0, st));
+  W2V_TRY(layernorm_launch(w.x0, true, M, D, H.ln1.g, H.ln1.b, c.ln_eps, 0, w.u1, st));
+  W2V_TRY(gemm_plain(w.u1, M, D, H.win, 3 * D, H.bin, w.qkv, 3 * D, false, nullptr, "train.fwd", st));
+  W2V_TRY(attention_launch(w.qkv, B, T, c.head_heads, hd, out_len, scale, w.ctx, st, w.lse));
+  W2V_TRY(copy_f32_launch(w.x0, w.x1, M * D, st));
+  W2V_TRY(gemm_plain(w.ctx, M, D, H.wo, D, H.bo, w.x1, D, true, w.x1, "train.fwd", st));
+  W2V_TRY(layernorm_launch(w.x1, true, M, D, H.ln2.g, H.ln2.b, c.ln_eps, 0, w.u2, st));
+  W2V_TRY(gemm_plain(w.u2, M, D, H.w1, F, H.b1, w.z1, F, false, nullptr, "train.fwd", st));
+  W2V_TRY(gelu_fwd_launch(w.z1, w.m, M * F, st));
+  W2V_TRY(copy_f32_launch(w.x1, w.x2, M * D, st));
+  W2V_TRY(gemm_plain(w.m, M, F, H.w2, D, H.b2, w.x2, D, true, w.x2, "train.fwd", st));
+
+  // ---------------- loss + backward
+  W2V_TRY(head_loss_backward_launch(w.x2, B, T, H.lnf.g, H.lnf.b, c.ln_eps, H.wout, H.bout, out_len, target,
+                                    pos_weight, w.dx2, w.dx2b, w.dlogit, w.st2, logits_out, w.loss_rows, loss_out, st));
+  W2V_TRY(final_param_grads_launch(w.dlogit, w.x2, w.st2, M, D, H.lnf.g, H.lnf.b, H.wout, w.red, kRedFloats, w.tmpA,
+                                   w.tmpS, G("head.out.weight"), G("head.ln_f.weight"), G("head.ln_f.bias"),
+                                   G("head.out.bias"), st));
+  // FFN: x2 = x1 + gelu(u2 W1^T + b1) W2^T + b2
+  W2V_TRY(colsum_launch(w.dx2, false, D, M, D, w.red, kRedFloats, G("head.ff2.bias"), st));
+  W2V_TRY(wgrad(w.dx2b, D, D, w.m, F, F, M, w, G("head.ff2.weight"), st));
+  W2V_TRY(dgrad(w.dx2b, M, D, H.w2, F, F, w, w.dm, st));
+  W2V_TRY(gelu_bwd_launch(w.z1, w.dm, w.dz1, M * F, st));
+  W2V_TRY(colsum_launch(w.dz1, true, F, M, F, w.red, kRedFloats, G("head.ff1.bias"), st));
+  W2V_TRY(wgrad(w.dz1, F, F, w.u2, D, D, M, w, G("head.ff1.weight"), st));
+  W2V_TRY(dgrad(w.dz1, M, F, H.w1, D, D, w, w.du2, st));
+  // LN2: dx1 = dx2 + LN2'(du2)
+  W2V_TRY(layernorm_bwd_launch(w.x1, w.du2, M, H.ln2.g, c.ln_eps, w.dx2, w.dx1, w.dx1b, w.st1, st));
+  W2V_TRY(ln_param_grads_launch(w.du2, w.x1, w.st1, M, D, w.red, kRedFloats, G("head.ln2.weight"), G("head.ln2.bias"), st));
+  // attention output projection: x1 = x0 + ctx Wo^T + bo
+  W2V_TRY(colsum_launch(w.dx1, false, D, M, D, w.red, kRedFloats, G("head.o.bias"), st));
+  W2V_TRY(wgrad(w.dx1b, D, D, w.ctx, D, D, M, w, G("head.o.weight"), st));
+  W2V_TRY(dgrad(w.dx1b, M, D, H.wo, D, D, w, w.dctx, st));
+  // attention
+  W2V_TRY(attention_bwd_launch(w.qkv, w.ctx, w.dctx, w.lse, w.delta, B, T, c.head_heads, hd, out_len, scale, w.dqkv, st));
+  // input projection: qkv = u1 Win^T + bin
+  W2V_TRY(colsum_launch(w.dqkv, true, 3 * D, M, 3 * D, w.red, kRedFloats, G("head.in_proj.bias"), st));
+  W2V_TRY(wgrad(w.dqkv, 3 * D, 3 * D, w.u1, D, D, M, w, G("head.in_proj.weight"), st));
+  W2V_TRY(dgrad(w.dqkv, M, 3 * D, H.win, D, D, w, w.du1, st));
+  // LN1 parameters (the encoder is frozen: no gradient flows into x0)
+  W2V_TRY(layernorm_bwd_launch(w.x0, w.du1, M, H.ln1.g, c.ln_eps, nullptr, nullptr, nullptr, w.st0, st));
+  W2V_TRY(ln_param_grads_launch(w.du1, w.x0, w.st0, M, D, w.red, kRedFloats, G("head.ln1.weight"), G("head.ln1.bias"), st));
+  return 0;
 }
 
 }  // extern "C"

@@ -59,8 +59,15 @@ int head_final_launch(const float* y, int B, int R, int C, const float* gamma, c
                       const int32_t* included, cudaStream_t s);
 
 // fused non-causal attention, key-length masked (HF:500-549; torch MHA in lib/models.py:291-300)
+// lse (optional, fp32 [B, heads, R]): per-row log-sum-exp in the log2 domain, for attention_bwd_launch
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
-                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s);
+                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s,
+                     float* lse = nullptr);
+// backward of the same attention (head training step, attention_bwd.cu): dqkv bf16 [B*R, 3*D] (dQ | dK | dV)
+// from dctx bf16 [B*R, D], the forward's qkv / ctx and lse. delta: fp32 [B, heads, R] scratch.
+int attention_bwd_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
+                         const float* lse, float* delta, int B, int R, int heads, int head_dim,
+                         const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, cudaStream_t s);
 
 // same contract, tcgen05 / TMEM / TMA implementation (attention_tc.cu) — the product path
 int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
