@@ -36,7 +36,7 @@ struct KernelArgs {
 // One epilogue warp, one accumulator tile: rows rg0..rg0+31 (TMEM lane quarter of this warp),
 // COLS columns starting at colbase. `wait_full` is invoked after the residual prefetch has been
 // issued and must block until the accumulator is complete (mbarrier wait + tcgen05 fence).
-template <int COLS, bool OUT_F32, int TMA_BUFS = 2, typename WaitFull>
+template <int COLS, bool OUT_F32, int TMA_BUFS = 2, int F32_BUFS = 1, typename WaitFull>
 __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0, long long orow0,
                                                    int colbase, uint32_t t_base, uint32_t stage,
                                                    int lane, WaitFull&& wait_full, int trace_it = -1,
@@ -202,12 +202,17 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
     // instead of 8 x (LDS.128 + RED.v4) per thread
     bool red_tma = false;
     if constexpr (OUT_F32) red_tma = use_red && tmap_o != nullptr;
-    if (red_tma) {   // the previous block's reduction must have finished READING the staging buffer
-      if (lane == 0) bulk_wait_group_read0();
+    // F32_BUFS 4 KB staging blocks used round-robin (NUNIT per tile is a multiple of F32_BUFS): before one is
+    // overwritten, all but the F32_BUFS-1 newest reductions must have finished READING their blocks
+    const uint32_t sblk = stage + (uint32_t)((F32_BUFS > 1 && red_tma ? (u % F32_BUFS) : 0) * 4096);
+    if (red_tma) {
+      if (lane == 0) {
+        if constexpr (F32_BUFS == 2) bulk_wait_group_read1(); else bulk_wait_group_read0();
+      }
       __syncwarp();
     }
     // row-per-thread -> staging (row = lane, 8 chunks of 16 B, chunk index XOR row%8)
-    const uint32_t srow = stage + (uint32_t)(lane * 128);
+    const uint32_t srow = sblk + (uint32_t)(lane * 128);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint32_t w0, w1, w2, w3;
@@ -233,7 +238,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const KernelArgs& p, int rg0,
       __syncwarp();
       if (u == 0) W2V_TR(7, trace_it);
       if (lane == 0) {
-        tma_reduce_add_2d(tmap_o, stage, col0, (int)orow0);   // rows past the end are clipped
+        tma_reduce_add_2d(tmap_o, sblk, col0, (int)orow0);   // rows past the end are clipped
         bulk_commit_group();
       }
       continue;

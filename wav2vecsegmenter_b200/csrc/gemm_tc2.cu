@@ -31,20 +31,33 @@ constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = HALF_N * BLOCK_K * 2;    // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-#ifndef W2V_PAIR_STAGES
-#define W2V_PAIR_STAGES 6
+// Operand ring depth and epilogue staging per warp: 6 stages + 4 KB (bf16 output: two 2 KB halves for the TMA
+// stores; fp32 in-place residual: one 4 KB block per TMA reduce-add). -DW2V_PAIR_F32_STAGES=5 gives the fp32
+// kernel TWO 4 KB staging blocks (the reduce-add of block u reads its block while block u+1 is staged) at the
+// price of one ring stage: measured SLOWER (attn_out in place 28.2 -> 30.0 us, ffn_down 95.0 -> 95.4 us,
+// profiles/experiments_r02.md), so the default stays 6.
+#ifndef W2V_PAIR_F32_STAGES
+#define W2V_PAIR_F32_STAGES 6
 #endif
-constexpr int STAGES = W2V_PAIR_STAGES;
-constexpr int STAGE_BUF = STAGES == 6 ? 4096 : 8192;   // epilogue staging per warp (5 stages free 32 KB)
-constexpr int TMA_BUFS = STAGE_BUF / 2048;
+template <bool OUT_F32>
+struct PairCfg {
+  static constexpr int STAGES = OUT_F32 ? W2V_PAIR_F32_STAGES : 6;
+  static constexpr int STAGE_BUF = STAGES == 6 ? 4096 : 8192;
+  static constexpr int TMA_BUFS = 2;                       // bf16 path: 2 KB halves of the first 4 KB
+  static constexpr int F32_BUFS = STAGE_BUF / 4096;        // fp32 path: 4 KB blocks
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * STAGE_BUF;
+};
 constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumulators
 constexpr int THREADS = 320;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * STAGE_BUF;
 
 template <bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_o, const KernelArgs p) {
+  constexpr int STAGES = PairCfg<OUT_F32>::STAGES;
+  constexpr int STAGE_BUF = PairCfg<OUT_F32>::STAGE_BUF;
+  constexpr int TMA_BUFS = PairCfg<OUT_F32>::TMA_BUFS;
+  constexpr int F32_BUFS = PairCfg<OUT_F32>::F32_BUFS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -173,7 +186,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const long long orow0 = (long long)g * p.o_group_rows + rg0;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)(acc * BLOCK_N + half * COLS);
-      gemm_epilogue_warp<COLS, OUT_F32, TMA_BUFS>(p, rg0, orow0, nb * BLOCK_N + half * COLS, t_base, stage_buf,
+      gemm_epilogue_warp<COLS, OUT_F32, TMA_BUFS, F32_BUFS>(p, rg0, orow0, nb * BLOCK_N + half * COLS, t_base, stage_buf,
                                         lane, [&] {
                                           if (warp == 2) W2V_TR(0, it);
                                           mbar_wait(&tfull_bar[acc], acc_phase);
@@ -242,8 +255,8 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   a.mask_len = g.mask_len; a.mask_period = g.mask_period > 0 ? g.mask_period : 1;
 
   W2V_ONCE_BEGIN
-  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<true>::SMEM_BYTES));
+  W2V_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<false>::SMEM_BYTES));
   W2V_ONCE_END
   const long long num_tiles = (long long)a.num_groups * a.tiles_m_per_group * (g.N / BLOCK_N);
   if (num_tiles == 0) return 0;
@@ -252,9 +265,9 @@ int gemm_tc2_launch(const GemmProblem& g, cudaStream_t stream) {
   {
     ProfScope ps(stream, "gemm_pair256");
     if (g.out_f32)
-      gemm_tc2_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
+      gemm_tc2_kernel<true><<<grid, THREADS, PairCfg<true>::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
     else
-      gemm_tc2_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
+      gemm_tc2_kernel<false><<<grid, THREADS, PairCfg<false>::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_o, a);
   }
   W2V_CHECK_LAUNCH();
   return 0;
