@@ -26,6 +26,8 @@
 // Rescaling is lazy (FlashAttention-4): the exponent's running max only advances when a tile max
 // exceeds it by more than 2^8. Replaces Wav2Vec2Attention's softmax(QK^T*scale + key mask) V
 // (HF:500-549).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -213,6 +215,8 @@ __device__ __forceinline__ void cursor_next(Cursor& c, const Walk& w) {
   cursor_skip_empty(c, w);
 }
 
+// 96 registers is the most two resident CTAs of 9 warps can have: the register file is allocated in units of two
+// warps, and with 104 registers (__maxnreg__) only ONE CTA fits per SM (measured: 99 -> 138 us).
 __global__ void __launch_bounds__(A6_THREADS, 2)
 attention_tc64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                       int R, int heads, int n_qt, int n_items, int B, Step step, const int* __restrict__ kv_len_g,
