@@ -1,3 +1,6 @@
+// NOTE (round 2): this first attempt UNDER-COUNTS the MUFU work — s[] and nm_hi do not change between iterations,
+// so the compiler hoists half of the exponentials out of the timed loop (it reports ~4 cycles per MUFU.EX2 instead of
+// the real 8). experiments/pipe_rates.cu (loop-carried chains) is the measurement to trust. Kept for the record.
 // Microbenchmark: how long does ONE warp need for the softmax exponential phase of a 16x128 S slice
 // (64 x [FFMA, MUFU.EX2, FADD] + 32 bf16x2 packs), alone on its SM sub-partition and with 1..3 sibling
 // warps on the same sub-partition? Answers whether the ~1100-cycle exp phase of attention_tc64 is a
