@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -61,9 +62,47 @@ int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t dim0, ui
   return make_tmap_2d_impl(out, base, dim0, dim1, row_stride_elems, box0, box1, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// Tensor maps are pure functions of (address, shape, strides, box, swizzle, type), and the forward pass asks for
+// the same ~400 of them every step (fixed workspace, fixed shapes): a small per-thread cache replaces the driver
+// call (cuTensorMapEncodeTiled) by a hash lookup. Entries never go stale: a map encodes no memory contents.
+namespace {
+struct TmapKey {
+  uint64_t base, dim0, dim1, dim2, s1, s2;
+  uint32_t box0, box1, sw, elem;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && dim0 == o.dim0 && dim1 == o.dim1 && dim2 == o.dim2 && s1 == o.s1 && s2 == o.s2 &&
+           box0 == o.box0 && box1 == o.box1 && sw == o.sw && elem == o.elem;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix(k.base); mix(k.dim0); mix(k.dim1); mix(k.dim2); mix(k.s1); mix(k.s2);
+    mix(((uint64_t)k.box0 << 32) | k.box1); mix(((uint64_t)k.sw << 32) | k.elem);
+    return (size_t)h;
+  }
+};
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> t_tmap_cache;
+constexpr size_t kTmapCacheMax = 4096;   // beyond this the cache is simply cleared (ragged shapes keep adding keys)
+bool tmap_cache_get(const TmapKey& k, CUtensorMap* out) {
+  auto it = t_tmap_cache.find(k);
+  if (it == t_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+void tmap_cache_put(const TmapKey& k, const CUtensorMap& m) {
+  if (t_tmap_cache.size() >= kTmapCacheMax) t_tmap_cache.clear();
+  t_tmap_cache.emplace(k, m);
+}
+}  // namespace
+
 static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
                              uint64_t row_stride_elems, uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw,
                              int elem_bytes) {
+  const TmapKey key = {reinterpret_cast<uint64_t>(base), dim0, dim1, 0, row_stride_elems, 0, box0, box1,
+                       (uint32_t)sw, (uint32_t)elem_bytes};
+  if (tmap_cache_get(key, out)) return 0;
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -97,11 +136,15 @@ static int make_tmap_2d_impl(CUtensorMap* out, const void* base, uint64_t dim0, 
               (unsigned long long)row_stride_elems, box0, box1);
     return W2VSEG_ERR_CUDA;
   }
+  tmap_cache_put(key, *out);
   return 0;
 }
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                       uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+  const TmapKey key = {reinterpret_cast<uint64_t>(base), dim0, dim1, dim2, stride1_elems, stride2_elems, box0, box1,
+                       (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B, 2u};
+  if (tmap_cache_get(key, out)) return 0;
   CUtensorMap probe;
   W2V_TRY(make_tmap_2d_bf16(&probe, base, dim0, dim1, stride1_elems, box0, box1));  // loads the encoder, checks alignment
   if ((stride2_elems * 2) % 16 != 0) {
@@ -120,6 +163,7 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
     set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
     return W2VSEG_ERR_CUDA;
   }
+  tmap_cache_put(key, *out);
   return 0;
 }
 
