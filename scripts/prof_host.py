@@ -31,3 +31,14 @@ for B in (14, 1):
     torch.cuda.synchronize()
     t_all = (time.perf_counter() - t0) / n
     print(f"B={B}: host enqueue {t_enq * 1e6:.0f} us per forward, {t_all * 1e3:.2f} ms per forward incl. GPU")
+for B in (1, 2):
+    g = eng.graphed(B, 320000)
+    g.audio.normal_(0, 0.1)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g.replay()
+    torch.cuda.synchronize()
+    print(f"B={B}: CUDA-graph replay {(time.perf_counter() - t0) / 20 * 1e3:.2f} ms per forward")

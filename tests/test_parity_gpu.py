@@ -180,3 +180,34 @@ def test_full_size_batch_properties():
     for i in (0, 9, 13):
         _, pi = eng.sfc_forward(dev[i: i + 1].contiguous(), [L], [L], ol[i: i + 1], L)
         assert (pi[0, : ol[i]] - p[i, : ol[i]]).abs().max().item() < 1e-5, i
+
+
+def test_cuda_graph_forward_matches_direct():
+    """the forward is capturable as it is (no allocation, no host synchronisation): a CUDA-graph replay gives
+    bit-identical probabilities, also after the inputs changed in place"""
+    import time
+
+    spec = synth.TINY
+    eng = engine_for(spec, 3)
+    B, L = 2, 64000
+    g = eng.graphed(B, L)
+    for seed in (5, 6):
+        raw = make_batch([L, 50000], seed).cuda()
+        lens = torch.tensor([L, 50000], dtype=torch.int32, device="cuda")
+        ol = torch.tensor([eng.num_frames(L), eng.num_frames(50000)], dtype=torch.int32, device="cuda")
+        g.audio.copy_(raw); g.sample_len.copy_(lens); g.out_len.copy_(ol)
+        p_graph = g.replay().clone()
+        _, p_direct = eng.sfc_forward(raw, lens, g.norm_len, ol, L)
+        torch.cuda.synchronize()
+        assert torch.equal(p_graph, p_direct)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g.replay()
+    torch.cuda.synchronize()
+    t_graph = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        eng.sfc_forward(g.audio, g.sample_len, g.norm_len, g.out_len, L, g.logits, g.probs)
+    torch.cuda.synchronize()
+    t_direct = (time.perf_counter() - t0) / 20
+    print(f"GRAPH tiny model, batch 2: graph replay {t_graph * 1e3:.3f} ms vs direct {t_direct * 1e3:.3f} ms per forward")

@@ -281,6 +281,10 @@ class SFCEngine:
         )
         return rows_out
 
+    def graphed(self, B: int, l_max: int) -> "GraphedForward":
+        """the fused forward for a FIXED batch shape captured into a CUDA graph (see GraphedForward)"""
+        return GraphedForward(self, B, l_max)
+
     # ------------------------------------------------------------------ talk-level reductions
     def scatter_rows(self, rows: torch.Tensor, start, count, n_frames: int, flag_col: int = -1) -> torch.Tensor:
         """rows fp32 [W, stride] -> talk vector fp64 [n_frames] (NaN where no window wrote);
@@ -316,6 +320,45 @@ class SFCEngine:
         nat.check(self.lib.w2vseg_moving_average(arr.data_ptr(), arr.numel(), int(window), out.data_ptr(),
                                                  self._stream()), "w2vseg_moving_average")
         return out
+
+
+class GraphedForward:
+    """`w2vseg_sfc_forward` for one fixed (B, l_max) captured into a CUDA graph: ONE graph launch instead of ~196
+    kernel launches. The forward allocates nothing and never synchronises, so it is capturable as it is. This is
+    the latency path: at batch 1-2 the step is bound by the host's launch rate (~12 us per launch, batch-1 forward
+    3.1 ms direct), not by the GPU; at the benchmark's batch 14 the step is GPU-bound and a graph changes nothing
+    (profiles/experiments_r01_s3.md). Usage: fill `.audio` / `.sample_len` / `.norm_len` / `.out_len` (static device
+    tensors) with copy_(), call `.replay()`, read `.probs` / `.logits` ([B, R])."""
+
+    def __init__(self, engine: SFCEngine, B: int, l_max: int):
+        self.engine = engine
+        dev = engine.device
+        self.B, self.l_max = int(B), int(l_max)
+        R = engine.frame_stride(l_max)
+        self.audio = torch.zeros(B, l_max, dtype=torch.float32, device=dev)
+        self.sample_len = torch.full((B,), l_max, dtype=torch.int32, device=dev)
+        self.norm_len = torch.full((B,), l_max, dtype=torch.int32, device=dev)
+        self.out_len = torch.full((B,), engine.num_frames(l_max), dtype=torch.int32, device=dev)
+        self.logits = torch.zeros(B, R, dtype=torch.float32, device=dev)
+        self.probs = torch.zeros(B, R, dtype=torch.float32, device=dev)
+        engine._workspace(B, l_max)                       # sized before capture: no allocation inside the graph
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up outside the capture (function attributes, tensor maps)
+            self._forward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._forward()
+
+    def _forward(self):
+        self.engine.sfc_forward(self.audio, self.sample_len, self.norm_len, self.out_len, self.l_max,
+                                logits_out=self.logits, probs_out=self.probs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.probs
 
 
 def moving_average_device(arr, window: int, device=None):
