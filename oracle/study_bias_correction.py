@@ -1,4 +1,4 @@
-"""CPU study: does per-layer BIAS CORRECTION (b' = b - (bf16(W) - W) @ mean_x, mean_x from a calibration
+"""TEST / ANALYSIS INFRASTRUCTURE (oracle side, never imported by the product path). CPU study: does per-layer BIAS CORRECTION (b' = b - (bf16(W) - W) @ mean_x, mean_x from a calibration
 signal) remove the frame-independent logit offset that bf16 weight rounding causes — on a DIFFERENT signal
 than the one calibrated on? fp32 arithmetic, weights rounded to bf16 (the CUDA path's configuration)."""
 import math
@@ -8,7 +8,7 @@ from pathlib import Path
 import torch
 import torch.nn.functional as F
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent   # oracle/ -> repo root
 sys.path.insert(0, str(ROOT))
 from oracle import sfc_oracle as so  # noqa: E402
 from wav2vecsegmenter_b200 import synth  # noqa: E402

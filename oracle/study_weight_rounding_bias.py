@@ -1,4 +1,4 @@
-"""CPU study (oracle, fp32 arithmetic): which weight groups' bf16 ROUNDING produces the frame-independent
+"""TEST / ANALYSIS INFRASTRUCTURE (oracle side, never imported by the product path). CPU study (oracle, fp32 arithmetic): which weight groups' bf16 ROUNDING produces the frame-independent
 logit offset of the large (24/24) configuration (profiles/parity_r01.md: +0.033)?
 Rounds one group of matrices at a time to bf16 and reports mean / std of the logit change."""
 import re
@@ -7,7 +7,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent   # oracle/ -> repo root
 sys.path.insert(0, str(ROOT))
 from oracle import sfc_oracle  # noqa: E402
 from wav2vecsegmenter_b200 import synth  # noqa: E402
