@@ -101,13 +101,36 @@ def generate(config, wav_paths=None, ckpt_path=None) -> list:
             assert sr == 16000, "Audio needs to have sample rate of 16000"
             yield wave
 
-    # pipelined over talks: decode + H2D of the next wav overlap the forward of the current one
     rank0 = int(os.environ.get("RANK", "0")) == 0
-    for wav_path, result in zip(wav_paths, runner.run_stream(waves())):
-        if not rank0:      # every rank holds the gathered probabilities; only rank 0 segments and writes
-            continue
-        segments = run_algorithm(config, result.probs)
-        yaml_content = update_yaml_content(yaml_content, segments, Path(wav_path).name)
+    if world == 1:
+        # one GPU: pipelined over talks — decode + H2D of the next wav overlap the forward of the current one
+        for wav_path, result in zip(wav_paths, runner.run_stream(waves())):
+            segments = run_algorithm(config, result.probs)
+            yaml_content = update_yaml_content(yaml_content, segments, Path(wav_path).name)
+    else:
+        # several GPUs: shard the windows of MANY talks at once (per-talk sharding would leave every rank with a
+        # handful of windows and one gather per talk): groups of talks of up to W2VSEG_GROUP_SECONDS of audio
+        # (default 2 h = 460 MB of host samples), one all_gather per group, rank 0 assembles, segments and writes
+        budget = float(os.environ.get("W2VSEG_GROUP_SECONDS", "7200")) * 16000
+        group_paths, group_waves, total = [], [], 0
+
+        def flush():
+            nonlocal yaml_content, group_paths, group_waves, total
+            if group_waves:
+                results = runner.run(group_waves, results_on=0)
+                if rank0:
+                    for wp, res in zip(group_paths, results):
+                        segments = run_algorithm(config, res.probs)
+                        yaml_content = update_yaml_content(yaml_content, segments, Path(wp).name)
+            group_paths, group_waves, total = [], [], 0
+
+        for wav_path, wave in zip(wav_paths, waves()):
+            if group_waves and total + len(wave) > budget:
+                flush()
+            group_paths.append(wav_path)
+            group_waves.append(wave)
+            total += len(wave)
+        flush()
     del model
     torch.cuda.empty_cache()
     return yaml_content
