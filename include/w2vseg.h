@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define W2VSEG_ABI_VERSION 2
+#define W2VSEG_ABI_VERSION 3
 
 #define W2VSEG_OK 0
 #define W2VSEG_ERR_ARG (-1)    /* bad argument / shape */
@@ -75,6 +75,11 @@ typedef struct w2vseg_config {
    *   conv_bias = 0: the convs have no bias (fe.conv{l}.bias do not exist)                     */
   int32_t feat_group_norm;
   int32_t conv_bias;
+  /* encoder layer variant (HF Wav2Vec2Config.do_stable_layer_norm):
+   *   post_layer_norm = 0: pre-LN "stable layer norm" layers (XLS-R, wav2vec2-large-lv60; HF:632-655)
+   *   post_layer_norm = 1: h = LN(h + Attn(h)); h = LN(h + FFN(h)) (wav2vec2-base / -large-960h; HF:575-609);
+   *                        no FFN adapters (n_adapter_layers must be 0)                               */
+  int32_t post_layer_norm;
 } w2vseg_config;
 
 /* ---- library ------------------------------------------------------------------------------ */

@@ -68,6 +68,22 @@ class _EngineHolder:
         return eng
 
 
+def _encoder_is_post_ln(name: str) -> bool:
+    """HF config.do_stable_layer_norm of the pretrained encoder (the checkpoint keys do not reveal it: pre-LN and
+    post-LN layers have the same parameters). W2VSEG_POST_LN=0/1 overrides (offline / random-init runs)."""
+    env = os.environ.get("W2VSEG_POST_LN")
+    if env is not None:
+        return env == "1"
+    if os.environ.get("W2VSEG_RANDOM_INIT", "0") == "1":
+        return False
+    try:
+        from transformers import Wav2Vec2Config
+
+        return not Wav2Vec2Config.from_pretrained(name).do_stable_layer_norm
+    except Exception:       # no local copy of the config: the reference's models are all XLS-R (pre-LN)
+        return False
+
+
 def _pretrained_encoder_state(name: str, spec: ModelSpec) -> dict:
     """weights of the pretrained wav2vec 2.0 / XLS-R encoder (the reference downloads them in
     HFWav2Vec2.__init__, lib/models.py:334). Sources, in order: a local directory / HF cache via
@@ -79,10 +95,9 @@ def _pretrained_encoder_state(name: str, spec: ModelSpec) -> dict:
     from transformers import Wav2Vec2Model
 
     hf = Wav2Vec2Model.from_pretrained(name)
-    if not getattr(hf.config, "do_stable_layer_norm", True):
-        raise NotImplementedError("post-LayerNorm encoders (do_stable_layer_norm=False: wav2vec2-base / -large-960h) "
-                                  "are not supported by the CUDA path; both feature-extractor variants "
-                                  "(feat_extract_norm 'layer' and 'group') are")
+    if hf.config.hidden_size != spec.hidden:
+        raise NotImplementedError(f"hidden size {hf.config.hidden_size} is not supported by the CUDA path (1024 only: "
+                                  "XLS-R-300m / wav2vec2-large geometry)")
     return {"wav2vec_model.model." + k: v for k, v in hf.state_dict().items()}
 
 
@@ -135,6 +150,12 @@ class SHAS(nn.Module):
         super().__init__()
         spec = ModelSpec.from_shas_kwargs(wav2vec_keep_layers, finetune_wav2vec, wav2vec_ft_layers,
                                           ffn_adapter, n_transformer_enc_layers, n_transformer_enc_heads)
+        if _encoder_is_post_ln(wav2vec_model_name):
+            # wav2vec2-base / -large-960h layers; the reference's adapter layer class exists for the stable-LN
+            # layer only (lib/models.py:390-428), so finetune + ffn_adapter cannot be combined with them
+            if spec.adapter_layers:
+                raise NotImplementedError("FFN adapters need a stable-LayerNorm (pre-LN) encoder such as XLS-R")
+            spec = dataclasses.replace(spec, post_ln=True)
         assert spec.hidden == HIDDEN_SIZE
         self.spec = spec
         self._holder = _EngineHolder(spec)

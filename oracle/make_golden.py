@@ -43,7 +43,10 @@ def build_reference_model(ns, spec: synth.ModelSpec, seed: int):
 
     finetune = spec.adapter_layers > 0
     name = "facebook/wav2vec2-xls-r-300m"
-    if spec.feat_norm == "group":
+    if spec.post_ln:
+        assert spec.feat_norm == "group" and not spec.conv_bias
+        name = ref_shims.POST_LN_NAME
+    elif spec.feat_norm == "group":
         name = ref_shims.GROUP_NORM_NAME if spec.conv_bias else ref_shims.GROUP_NORM_NOBIAS_NAME
     m = ns.models.SHAS(name, spec.keep_layers, finetune,
                        spec.adapter_layers if finetune else 99, False, False, True,
@@ -82,7 +85,7 @@ def gold_batch(ns, name, spec, seed, lens, audio_seed):
     np.savez_compressed(
         GOLD / f"{name}.npz",
         spec=np.array([spec.keep_layers, spec.adapter_layers, spec.head_layers, spec.head_heads,
-                       int(spec.feat_norm == "group"), int(spec.conv_bias)]),
+                       int(spec.feat_norm == "group"), int(spec.conv_bias), int(spec.post_ln)]),
         seed=seed, audio_seed=audio_seed, lens=np.array(lens),
         hidden_frames=np.array(frames), hidden=hidden[:, frames, :].numpy().astype(np.float32),
         hidden_T=hidden.shape[1],
@@ -398,6 +401,8 @@ def main():
         # the GroupNorm statistics run over the PADDED row, so the padding of the batch matters
         "tiny_gn_batch": lambda: gold_batch(ns, "tiny_gn_batch", synth.TINY_GN, 0, [64000, 113234, 48000], 70),
         "tiny_gn_nobias_batch": lambda: gold_batch(ns, "tiny_gn_nobias_batch", synth.TINY_GN_NOBIAS, 0, [160000, 90001], 71),
+        # wav2vec2-large-960h-like architecture: GroupNorm extractor, no conv bias, post-LN encoder layers (3 kept)
+        "tiny_postln_batch": lambda: gold_batch(ns, "tiny_postln_batch", synth.TINY_POSTLN, 0, [96000, 57011], 72),
         # BASELINE.json configs[0]: middle (0/16), frozen encoder, single 20 s window
         "middle_window": lambda: gold_batch(ns, "middle_window", synth.MIDDLE, 0, [320000], 20),
         # middle+half (8/16): adapters in layers 8..15, ragged pair

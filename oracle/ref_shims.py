@@ -31,9 +31,10 @@ def reference_available() -> bool:
 
 GROUP_NORM_NAME = "synthetic/xls-r-300m-group-norm"          # feat_extract_norm="group", conv_bias=True
 GROUP_NORM_NOBIAS_NAME = "synthetic/xls-r-300m-group-norm-nobias"
+POST_LN_NAME = "synthetic/wav2vec2-large-960h-like"         # group norm, no conv bias, post-LN encoder layers
 
 
-def xlsr_config(feat_extract_norm="layer", conv_bias=True):
+def xlsr_config(feat_extract_norm="layer", conv_bias=True, stable_ln=True):
     from transformers import Wav2Vec2Config
 
     return Wav2Vec2Config(
@@ -51,7 +52,7 @@ def xlsr_config(feat_extract_norm="layer", conv_bias=True):
         conv_stride=(5, 2, 2, 2, 2, 2, 2),
         num_conv_pos_embeddings=128,
         num_conv_pos_embedding_groups=16,
-        do_stable_layer_norm=True,
+        do_stable_layer_norm=stable_ln,
         mask_time_prob=0.075,
     )
 
@@ -93,6 +94,8 @@ def install():
                 return xlsr_config("group", True)
             if name == GROUP_NORM_NOBIAS_NAME:
                 return xlsr_config("group", False)
+            if name == POST_LN_NAME:
+                return xlsr_config("group", False, stable_ln=False)
             return xlsr_config()
 
         Wav2Vec2Model.from_pretrained = classmethod(lambda cls, name, *a, **k: cls(_cfg(name)))

@@ -105,7 +105,8 @@ def _mha(x, wq, bq, wk, bk, wv, bv, wo, bo, n_heads, key_valid):
     return a.transpose(1, 2).reshape(B, T, D) @ wo.t() + bo
 
 
-def encoder(sd, audio: torch.Tensor, sample_lens, keep_layers: int, n_heads: int = 16) -> torch.Tensor:
+def encoder(sd, audio: torch.Tensor, sample_lens, keep_layers: int, n_heads: int = 16,
+            post_ln: bool = False) -> torch.Tensor:
     """model.wav2vec_model(audio, in_mask) of lib/evaluate.py:59, i.e. HFWav2Vec2[WithAdapter]
     (lib/models.py:322-368, 431-485) around Wav2Vec2Model.forward (HF:1327-1383):
     audio [B, L] (already normalised), sample_lens[b] = in_mask[b].sum(). Returns [B, T, 1024]."""
@@ -130,6 +131,19 @@ def encoder(sd, audio: torch.Tensor, sample_lens, keep_layers: int, n_heads: int
     for i in range(keep_layers):                                              # HF:770-784
         p = f"{W2V}encoder.layers.{i}."
         g = lambda k: _get(sd, p + k, dtype)  # noqa: E731
+        if post_ln:
+            # do_stable_layer_norm = False (wav2vec2-base / -large-960h): HF Wav2Vec2EncoderLayer.forward;
+            # encoder.layer_norm (applied BEFORE the layers in this variant) is an Identity in the reference
+            # (lib/models.py:349), so the first layer sees the un-normalised positional-conv output
+            z = z + _mha(z, g("attention.q_proj.weight"), g("attention.q_proj.bias"),
+                         g("attention.k_proj.weight"), g("attention.k_proj.bias"),
+                         g("attention.v_proj.weight"), g("attention.v_proj.bias"),
+                         g("attention.out_proj.weight"), g("attention.out_proj.bias"), n_heads, valid)
+            z = F.layer_norm(z, (z.shape[-1],), g("layer_norm.weight"), g("layer_norm.bias"), 1e-5)
+            ff = F.gelu(z @ g("feed_forward.intermediate_dense.weight").t() + g("feed_forward.intermediate_dense.bias"))
+            z = z + ff @ g("feed_forward.output_dense.weight").t() + g("feed_forward.output_dense.bias")
+            z = F.layer_norm(z, (z.shape[-1],), g("final_layer_norm.weight"), g("final_layer_norm.bias"), 1e-5)
+            continue
         u = F.layer_norm(z, (z.shape[-1],), g("layer_norm.weight"), g("layer_norm.bias"), 1e-5)
         z = z + _mha(u, g("attention.q_proj.weight"), g("attention.q_proj.bias"),
                      g("attention.k_proj.weight"), g("attention.k_proj.bias"),
@@ -167,11 +181,11 @@ def head(sd, hidden: torch.Tensor, out_mask: torch.Tensor, n_heads: int = 8, pre
     return (x @ g("output_layer.weight").t() + g("output_layer.bias")).squeeze(-1)
 
 
-def batch_probs(sd, audio, sample_lens, out_mask, keep_layers, head_heads=8):
+def batch_probs(sd, audio, sample_lens, out_mask, keep_layers, head_heads=8, post_ln=False):
     """the per-batch body of lib.evaluate.infer (lib/evaluate.py:58-91) for loss_tag 'bce':
     returns (probs [B, T'], logits [B, T'], out_mask', ends_shift) where ends_shift = 1 if the
     reference decrements every `end` of the batch (:66-68)."""
-    hidden = encoder(sd, audio, sample_lens, keep_layers)
+    hidden = encoder(sd, audio, sample_lens, keep_layers, post_ln=post_ln)
     ends_shift = 0
     size1, size2 = hidden.shape[1], out_mask.shape[1]
     if size1 != size2:

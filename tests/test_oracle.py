@@ -14,7 +14,8 @@ from wav2vecsegmenter_b200 import synth
 from util import load_gold, make_batch, spec_of
 
 
-@pytest.mark.parametrize("name", ["tiny_batch", "middle_window", "tiny_gn_batch", "tiny_gn_nobias_batch"])
+@pytest.mark.parametrize("name", ["tiny_batch", "middle_window", "tiny_gn_batch", "tiny_gn_nobias_batch",
+                                  "tiny_postln_batch"])
 def test_forward_oracle_matches_reference(name):
     g = load_gold(name)
     spec = spec_of(g)
@@ -29,12 +30,13 @@ def test_forward_oracle_matches_reference(name):
         out_mask[i, :n] = True
     torch.set_num_threads(8)
     with torch.no_grad():
-        hidden = sfc_oracle.encoder(sd, norm, lens, spec.keep_layers)
+        hidden = sfc_oracle.encoder(sd, norm, lens, spec.keep_layers, post_ln=spec.post_ln)
         assert hidden.shape[1] == int(g["hidden_T"])
         ref_h = g["hidden"]
         rel = np.abs(hidden[:, g["hidden_frames"]].numpy() - ref_h).max() / np.abs(ref_h).max()
         assert rel < 2e-4, rel
-        probs, logits, mask, _ = sfc_oracle.batch_probs(sd, norm, lens, out_mask, spec.keep_layers, spec.head_heads)
+        probs, logits, mask, _ = sfc_oracle.batch_probs(sd, norm, lens, out_mask, spec.keep_layers, spec.head_heads,
+                                                        post_ln=spec.post_ln)
     assert (mask.numpy() == g["out_mask"]).all()
     assert np.abs(probs.numpy() - g["probs"]).max() < 2e-4
     assert np.abs(logits.numpy() - g["logits"]).max() < 2e-3

@@ -33,7 +33,7 @@ def engine_for(spec, seed):
 
 
 @pytest.mark.parametrize("name", ["tiny_batch", "middle_window", "middle_half_batch", "large_batch",
-                                  "tiny_gn_batch", "tiny_gn_nobias_batch"])
+                                  "tiny_gn_batch", "tiny_gn_nobias_batch", "tiny_postln_batch"])
 def test_probs_match_reference_golden(name):
     g = load_gold(name)
     spec = spec_of(g)
@@ -67,7 +67,7 @@ def test_probs_match_reference_golden(name):
         assert err <= 1e-2, f"{name}: max-abs prob err {err}"
 
 
-@pytest.mark.parametrize("name", ["tiny_batch", "middle_half_batch", "tiny_gn_batch"])
+@pytest.mark.parametrize("name", ["tiny_batch", "middle_half_batch", "tiny_gn_batch", "tiny_postln_batch"])
 def test_hidden_and_two_call_path_match_golden(name):
     """model.wav2vec_model(...) then model.seg_model(...) as two calls (lib/evaluate.py:59,72)"""
     g = load_gold(name)

@@ -18,6 +18,8 @@ def spec_of(g):
     extra = {}
     if len(g["spec"]) > 4:
         extra = {"feat_norm": "group" if int(g["spec"][4]) else "layer", "conv_bias": bool(int(g["spec"][5]))}
+        if len(g["spec"]) > 6:
+            extra["post_ln"] = bool(int(g["spec"][6]))
     return synth.ModelSpec(keep_layers=k, adapter_layers=a, head_layers=hl, head_heads=hh, **extra)
 
 

@@ -14,7 +14,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("W2VSEG_LIB") or Path(__file__).resolve().parent / "csrc" / "libw2vseg.so")
 
 _lib = None
-ABI_VERSION = 2   # W2VSEG_ABI_VERSION of include/w2vseg.h this binding was written against
+ABI_VERSION = 3   # W2VSEG_ABI_VERSION of include/w2vseg.h this binding was written against
 
 
 class W2VSegError(RuntimeError):
@@ -41,6 +41,7 @@ class Config(C.Structure):
         ("ln_eps", C.c_float),
         ("feat_group_norm", C.c_int32),
         ("conv_bias", C.c_int32),
+        ("post_layer_norm", C.c_int32),
     ]
 
 

@@ -234,8 +234,12 @@ void build_layout(w2vseg_handle* h) {
     L.wqkv = h->alloc<bf16>((size_t)3 * D * D);
     float* bqkv_raw = add_bias(h, "", &L.bqkv, 3 * D);
     const char* qkvn[3] = {".q", ".k", ".v"};
+    // post-LN encoder, layer 0: q/k/v read the un-normalised output of the positional conv (no per-frame
+    // LayerNorm in front of them): a calibrated mean does not carry over, no bias correction (cf. the GroupNorm convs)
+    const bool qkv_corr = !(c.post_layer_norm && i == 0);
     for (int j = 0; j < 3; ++j) {
-      add_mat(h, p + qkvn[j] + ".weight", L.wqkv + (size_t)j * D * D, D, D, D, 1.f, L.bqkv + (size_t)j * D, L.x.ln1);
+      add_mat(h, p + qkvn[j] + ".weight", L.wqkv + (size_t)j * D * D, D, D, D, 1.f,
+              qkv_corr ? L.bqkv + (size_t)j * D : nullptr, L.x.ln1);
       Slot s; s.kind = SLOT_VEC; s.numel = D; s.fdst = bqkv_raw + (size_t)j * D;
       h->slots[p + qkvn[j] + ".bias"] = s;
     }
@@ -431,9 +435,15 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
   }
 
   // transformer layers (pre-LN "stable layer norm" variant, HF:632-655; adapter lib/models.py:404-428)
+  const bool post_ln = c.post_layer_norm != 0;
+  // post-LN encoder (do_stable_layer_norm = False, HF Wav2Vec2EncoderLayer): h = LN1(h + Attn(h)); h = LN2(h + FFN(h)).
+  // The attention / FFN inputs are the residual stream itself, so every LayerNorm writes fp32 (in place) AND the
+  // bf16 copy the next GEMM reads; only the first layer needs a separate cast (encoder.layer_norm is an Identity in
+  // the reference, lib/models.py:349).
+  if (post_ln && c.n_layers > 0) W2V_TRY(cast_to_padded_launch(w.h, B, R, D, 0, w.xn, st));
   for (int i = 0; i < c.n_layers; ++i) {
     const EncLayerW& L = h->enc[i];
-    W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln1.g, L.ln1.b, c.ln_eps, 0, w.xn, st));
+    if (!post_ln) W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln1.g, L.ln1.b, c.ln_eps, 0, w.xn, st));
     {
       GemmProblem g = linear(w.xn, M, D, L.wqkv, 3 * D, L.bqkv);
       g.out = w.qkv; g.ld_out = 3 * D;
@@ -450,7 +460,8 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       prof_tag("gemm.attn_out");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
-    W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln2.g, L.ln2.b, c.ln_eps, 0, w.xn, st));
+    if (post_ln) W2V_TRY(layernorm_dual_launch(w.h, M, L.ln1.g, L.ln1.b, c.ln_eps, w.xn, st));
+    else W2V_TRY(layernorm_launch(w.h, true, M, D, L.ln2.g, L.ln2.b, c.ln_eps, 0, w.xn, st));
     {
       GemmProblem g = linear(w.xn, M, D, L.w1, L.F1, L.b1);
       g.act_split = c.ffn; g.act_lo = ACT_GELU; g.act_hi = ACT_RELU;
@@ -466,6 +477,7 @@ int run_encoder(w2vseg_handle* h, const Workspace& w, const float* audio, int64_
       prof_tag("gemm.ffn_down");
       W2V_TRY(gemm_tc2_launch(g, st));
     }
+    if (post_ln) W2V_TRY(layernorm_dual_launch(w.h, M, L.ln2.g, L.ln2.b, c.ln_eps, w.xn, st));
   }
   return 0;
 }
@@ -532,6 +544,8 @@ int32_t w2vseg_create(const w2vseg_config* cfg, w2vseg_handle** out) {
   W2V_REQUIRE(cfg->heads > 0 && cfg->hidden / cfg->heads == 64, "create: encoder head_dim must be 64");
   W2V_REQUIRE(cfg->n_layers >= 0 && cfg->n_adapter_layers >= 0 && cfg->n_adapter_layers <= cfg->n_layers,
               "create: bad layer counts (%d layers, %d adapters)", cfg->n_layers, cfg->n_adapter_layers);
+  W2V_REQUIRE(!(cfg->post_layer_norm && cfg->n_adapter_layers > 0),
+              "create: FFN adapters exist for the stable-LayerNorm encoder layer only (lib/models.py:390-428)");
   W2V_REQUIRE(cfg->ffn % 256 == 0 && cfg->adapter_dim % 256 == 0 && cfg->head_ffn % 256 == 0,
               "create: ffn/adapter/head_ffn sizes must be multiples of 256");
   W2V_REQUIRE(cfg->pos_kernel == 128 && cfg->pos_groups == 16, "create: positional conv must be k=128, g=16");

@@ -301,9 +301,12 @@ __device__ __forceinline__ void ln1024_load(float4 (&r)[8], const float* in, lon
   for (int i = 0; i < 8; ++i) r[i] = __ldcs(p + i * 32 + lane);   // streamed: read exactly once
 }
 
+// F32OUT: additionally write the normalised row in fp32 (post-LayerNorm encoders: the LayerNorm output IS the
+// residual stream; out_f32 may alias the input: the whole row is in registers before anything is written)
+template <bool F32OUT = false>
 __device__ __forceinline__ void ln1024_finish(const float4 (&r)[8], long long row, int lane,
                                               const float* gamma, const float* beta, float eps,
-                                              __nv_bfloat16* out) {
+                                              __nv_bfloat16* out, float* out_f32 = nullptr) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
@@ -325,16 +328,22 @@ __device__ __forceinline__ void ln1024_finish(const float4 (&r)[8], long long ro
                  : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(gamma + col));
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(bt.x), "=f"(bt.y), "=f"(bt.z), "=f"(bt.w) : "l"(beta + col));
-    const uint32_t u0 = pack_bf16x2(fmaf((r[i].x - mean) * rstd, g.x, bt.x), fmaf((r[i].y - mean) * rstd, g.y, bt.y));
-    const uint32_t u1 = pack_bf16x2(fmaf((r[i].z - mean) * rstd, g.z, bt.z), fmaf((r[i].w - mean) * rstd, g.w, bt.w));
+    const float y0 = fmaf((r[i].x - mean) * rstd, g.x, bt.x), y1 = fmaf((r[i].y - mean) * rstd, g.y, bt.y);
+    const float y2 = fmaf((r[i].z - mean) * rstd, g.z, bt.z), y3 = fmaf((r[i].w - mean) * rstd, g.w, bt.w);
+    const uint32_t u0 = pack_bf16x2(y0, y1);
+    const uint32_t u1 = pack_bf16x2(y2, y3);
     asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(out + row * 1024 + col), "r"(u0), "r"(u1) : "memory");
+    if constexpr (F32OUT)
+      asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_f32 + row * 1024 + col), "f"(y0), "f"(y1),
+                   "f"(y2), "f"(y3) : "memory");
   }
 }
 
+template <bool F32OUT>
 __global__ void __launch_bounds__(256, 2)
-layernorm1024_stream_kernel(const float* __restrict__ in, long long rows,
+layernorm1024_stream_kernel(const float* in, long long rows,
                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                            float eps, __nv_bfloat16* __restrict__ out) {
+                            float eps, __nv_bfloat16* __restrict__ out, float* out_f32) {
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * 8;
   long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -344,7 +353,7 @@ layernorm1024_stream_kernel(const float* __restrict__ in, long long rows,
   for (; row < rows; row += nw) {
     const bool more = row + nw < rows;
     if (more) ln1024_load(nxt, in, row + nw, lane);
-    ln1024_finish(cur, row, lane, gamma, beta, eps, out);
+    ln1024_finish<F32OUT>(cur, row, lane, gamma, beta, eps, out, out_f32);
     if (more) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
@@ -914,8 +923,8 @@ int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const flo
     } else {
       const long long want = (rows + 7) / 8;
       const long long cap = 2LL * num_sms();
-      layernorm1024_stream_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(
-          reinterpret_cast<const float*>(in), rows, gamma, beta, eps, out);
+      layernorm1024_stream_kernel<false><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(
+          reinterpret_cast<const float*>(in), rows, gamma, beta, eps, out, nullptr);
     }
   }
   else if (C == 1024 && !in_f32 && act == 0) W2V_LN(1024, false, 0);
@@ -924,6 +933,18 @@ int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const flo
     return W2VSEG_ERR_ARG;
   }
 #undef W2V_LN
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm_dual_launch(float* h, int64_t rows, const float* gamma, const float* beta, float eps,
+                          __nv_bfloat16* out_bf16, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  ProfScope ps(s, "layernorm");
+  const long long want = (rows + 7) / 8;
+  const long long cap = 2LL * num_sms();
+  layernorm1024_stream_kernel<true><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(h, rows, gamma, beta, eps,
+                                                                                        out_bf16, h);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -42,6 +42,10 @@ int conv0_tc_launch(const float* audio, int64_t audio_stride, const int32_t* sam
 int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const float* gamma,
                      const float* beta, float eps, int act, __nv_bfloat16* out, cudaStream_t s);
 
+// post-LayerNorm encoders: h (fp32 [rows, 1024]) = LayerNorm(h) in place, plus a bf16 copy for the next GEMM
+int layernorm_dual_launch(float* h, int64_t rows, const float* gamma, const float* beta, float eps,
+                          __nv_bfloat16* out_bf16, cudaStream_t s);
+
 // h fp32 [B*R, C] -> zpad bf16 [B*(R+pad2), C] interior rows (64-row zero halo each side is
 // memset by the caller). Feeds the positional conv (HF:360-368).
 int cast_to_padded_launch(const float* h, int B, int R, int C, int halo, __nv_bfloat16* zpad,

@@ -69,6 +69,7 @@ class SFCEngine:
             pos_groups=spec.pos_groups, head_layers=spec.head_layers, head_heads=spec.head_heads,
             head_ffn=spec.head_ffn, ln_eps=spec.ln_eps,
             feat_group_norm=int(spec.feat_norm == "group"), conv_bias=int(spec.conv_bias),
+            post_layer_norm=int(spec.post_ln),
         )
         h = nat.C.c_void_p()
         nat.check(self.lib.w2vseg_create(nat.C.byref(cfg), nat.C.byref(h)), "w2vseg_create")

@@ -39,6 +39,9 @@ class ModelSpec:
     # (XLS-R, HF:275-299), "group" = GroupNorm(512 groups) after conv 0 only (HF:302-323, 388-391)
     feat_norm: str = "layer"
     conv_bias: bool = True
+    # encoder layer variant (HF config.do_stable_layer_norm): False = pre-LN "stable layer norm" layers (XLS-R),
+    # True = post-LN layers h = LN(h + Attn(h)); h = LN(h + FFN(h)) (wav2vec2-base / -large-960h, HF:575-609)
+    post_ln: bool = False
 
     @staticmethod
     def from_shas_kwargs(wav2vec_keep_layers, finetune_wav2vec, wav2vec_ft_layers, ffn_adapter,
@@ -61,6 +64,8 @@ MIDDLE_HALF = ModelSpec(keep_layers=16, adapter_layers=8)     # middle+half (8/1
 TINY = ModelSpec(keep_layers=2, adapter_layers=1)             # test-sized
 TINY_GN = ModelSpec(keep_layers=2, adapter_layers=1, feat_norm="group")                     # GroupNorm extractor
 TINY_GN_NOBIAS = ModelSpec(keep_layers=2, adapter_layers=0, feat_norm="group", conv_bias=False)
+# the wav2vec2-large-960h architecture family: GroupNorm extractor without conv bias + post-LN encoder layers
+TINY_POSTLN = ModelSpec(keep_layers=3, adapter_layers=0, feat_norm="group", conv_bias=False, post_ln=True)
 
 
 def random_state_dict(spec: ModelSpec, seed: int = 0, logit_std: float = 2.0) -> dict:
