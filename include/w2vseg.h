@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define W2VSEG_ABI_VERSION 3
+#define W2VSEG_ABI_VERSION 4
 
 #define W2VSEG_OK 0
 #define W2VSEG_ERR_ARG (-1)    /* bad argument / shape */
@@ -217,8 +217,12 @@ int32_t w2vseg_sfc_forward_rows(w2vseg_handle* h, const float* audio, int64_t au
  *   hidden      device fp32, window b frame t at hidden + b*batch_stride + t*hidden_dim (as w2vseg_head)
  *   target      device fp32 [B, T] labels in [0, 1]
  *   loss_out    device fp32 [1]; logits_out device fp32 [B, T] or NULL (0 where masked)
- * Dropout (init_dropout and the layer's 0.1) is NOT applied: the step is the deterministic gradient of the
- * eval-mode head, which is what the parity tests compare with torch.autograd.
+ * Dropout (the head runs in train() mode in the reference: init_dropout on the encoder output,
+ * lib/models.py:309, and the TransformerEncoderLayer's own dropout on the attention weights, after the attention
+ * block, inside the FFN and after the FFN, lib/models.py:291-300): init_dropout / layer_dropout in [0, 1); masks
+ * are a counter-based hash of (seed, site, element index) — csrc/dropout.cuh — regenerated in the backward, never
+ * stored, so a step is reproducible from its seed and a test can rebuild the masks on the host. Pass a new seed
+ * every step. With both 0 the step is the deterministic gradient of the eval-mode head.
  * Arithmetic: bf16 GEMM operands (tcgen05, fp32 accumulate) for forward, dgrad and wgrad; attention backward
  * recomputes S / P from the forward's row log-sum-exp (mma.sync, attention_bwd.cu); LayerNorm, GELU', loss and
  * all reductions in fp32 with fixed summation orders (bit-reproducible). */
@@ -228,6 +232,7 @@ size_t w2vseg_head_train_workspace_bytes(const w2vseg_handle* h, int32_t B, int3
 int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t batch_stride, int32_t T,
                                const int32_t* out_len, const float* target, float pos_weight, int32_t B,
                                float* loss_out, float* logits_out, float* grads, size_t grads_floats,
+                               float init_dropout, float layer_dropout, uint32_t seed,
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- talk-level reductions (all device pointers) --------------------------------------------- */
@@ -298,14 +303,19 @@ int32_t w2vseg_attention_mma(const void* qkv_bf16, int32_t B, int32_t R, int32_t
                              void* stream);
 
 /* training forward of the head attention: w2vseg_attention_mma that also returns the per-row log-sum-exp
- * (fp32 [B, heads, R], log2 domain) the backward re-exponentiates with */
+ * (fp32 [B, heads, R], log2 domain) the backward re-exponentiates with. dropout in [0, 1) on the attention
+ * weights: element (b, h, q, k) is kept iff lowbias32((((b*heads + h)*R + q)*R + k) ^ key) >= dropout * 2^32,
+ * key = lowbias32(seed * 0x9E3779B9 + 1) (site 1 of csrc/dropout.cuh), and scaled by 1 / (1 - dropout). */
 int32_t w2vseg_attention_train(const void* qkv_bf16, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
-                               const int32_t* kv_len, float scale, void* ctx_bf16, float* lse, void* stream);
+                               const int32_t* kv_len, float scale, void* ctx_bf16, float* lse, float dropout,
+                               uint32_t seed, void* stream);
 /* attention backward: dqkv bf16 [B*R, 3*heads*head_dim] (dQ | dK | dV) from dctx bf16 [B*R, heads*head_dim],
- * the forward's qkv / ctx / lse; delta_scratch: fp32 [B, heads, R]. Rows >= kv_len[b] get zero dK / dV. */
+ * the forward's qkv / ctx / lse; delta_scratch: fp32 [B, heads, R]. Rows >= kv_len[b] get zero dK / dV.
+ * dropout / seed: the forward's. */
 int32_t w2vseg_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* dctx_bf16, const float* lse,
                              float* delta_scratch, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
-                             const int32_t* kv_len, float scale, void* dqkv_bf16, void* stream);
+                             const int32_t* kv_len, float scale, void* dqkv_bf16, float dropout, uint32_t seed,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, s), f"{s} declared in w2vseg.h but not exported"
         assert s in _native.SIGNATURES, f"{s} has no ctypes prototype"
     assert set(_native.SIGNATURES) == set(syms)
-    assert lib.w2vseg_abi_version() == _native.ABI_VERSION == 3
+    assert lib.w2vseg_abi_version() == _native.ABI_VERSION == 4
 
 
 def test_geometry_is_pure_host_arithmetic():

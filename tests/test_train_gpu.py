@@ -10,7 +10,7 @@ import torch
 from wav2vecsegmenter_b200 import _native as n
 from wav2vecsegmenter_b200 import synth
 from wav2vecsegmenter_b200.engine import SFCEngine
-from wav2vecsegmenter_b200.train import HeadTrainer
+from wav2vecsegmenter_b200.train import HeadTrainer, dropout_mask
 
 pytestmark = pytest.mark.gpu
 
@@ -19,8 +19,10 @@ def rel(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("heads,dh,R,lens", [(8, 128, 200, [200, 77]), (8, 128, 999, [999, 640, 5]), (16, 64, 130, [130, 64, 0])])
-def test_attention_backward_matches_autograd(heads, dh, R, lens):
+@pytest.mark.parametrize("heads,dh,R,lens,pdrop", [(8, 128, 200, [200, 77], 0.0), (8, 128, 999, [999, 640, 5], 0.0),
+                                                   (16, 64, 130, [130, 64, 0], 0.0), (8, 128, 333, [333, 120], 0.1),
+                                                   (16, 64, 130, [130, 64, 0], 0.25)])
+def test_attention_backward_matches_autograd(heads, dh, R, lens, pdrop):
     lib = n.load()
     B, D = len(lens), heads * dh
     g = torch.Generator(device="cuda").manual_seed(R + dh)
@@ -32,9 +34,10 @@ def test_attention_backward_matches_autograd(heads, dh, R, lens):
     delta = torch.empty(B, heads, R, device="cuda")
     dqkv = torch.full((B * R, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
     st = n.current_stream_ptr()
-    n.check(lib.w2vseg_attention_train(n.ptr(qkv), B, R, heads, dh, n.ptr(kv), dh ** -0.5, n.ptr(ctx), n.ptr(lse), st))
+    n.check(lib.w2vseg_attention_train(n.ptr(qkv), B, R, heads, dh, n.ptr(kv), dh ** -0.5, n.ptr(ctx), n.ptr(lse), pdrop, 11,
+                                       st))
     n.check(lib.w2vseg_attention_bwd(n.ptr(qkv), n.ptr(ctx), n.ptr(dctx), n.ptr(lse), n.ptr(delta), B, R, heads, dh,
-                                     n.ptr(kv), dh ** -0.5, n.ptr(dqkv), st))
+                                     n.ptr(kv), dh ** -0.5, n.ptr(dqkv), pdrop, 11, st))
     torch.cuda.synchronize()
     x = qkv.float().view(B, R, 3, heads, dh).requires_grad_(True)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))            # [B, H, R, dh]
@@ -42,6 +45,7 @@ def test_attention_backward_matches_autograd(heads, dh, R, lens):
     key_ok = torch.arange(R, device="cuda")[None, :] < kv[:, None]
     s = s.masked_fill(~key_ok[:, None, None, :], float("-inf"))
     p = torch.softmax(s, -1).nan_to_num(0.0)                              # windows without any key: zeros
+    p = p * dropout_mask(pdrop, 11, 1, B * heads * R * R, "cuda").view(B, heads, R, R)   # same masks as the kernel
     o = (p @ v).transpose(1, 2).reshape(B * R, D)
     assert rel(ctx, o.detach()) < 2e-2
     o.backward(dctx.float())
@@ -116,6 +120,68 @@ def test_head_train_step_matches_autograd():
     trainer.step_hidden(hidden, lens, target, pw)
     for k, p in trainer.params.items():
         assert torch.equal(p.grad, 2 * g1[k]), k
+    eng.close()
+
+
+def _manual_head(params, hidden, mask, heads, masks):
+    """the same head written out by hand (pre-norm TransformerEncoderLayer + LayerNorm + Linear) so that the five
+    dropout sites can use the CUDA step's own masks (`masks[site]`, flat factor tensors)"""
+    F = torch.nn.functional
+    P = params
+    B, T, D = hidden.shape
+    dh = D // heads
+    x0 = hidden * masks[0].view(B, T, D)
+    u1 = F.layer_norm(x0, (D,), P["transformer.layers.0.norm1.weight"], P["transformer.layers.0.norm1.bias"])
+    qkv = u1 @ P["transformer.layers.0.self_attn.in_proj_weight"].T + P["transformer.layers.0.self_attn.in_proj_bias"]
+    q, k, v = (t.view(B, T, heads, dh).transpose(1, 2) for t in qkv.chunk(3, -1))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1) * masks[1].view(B, heads, T, T)
+    ctx = (p @ v).transpose(1, 2).reshape(B, T, D)
+    y = ctx @ P["transformer.layers.0.self_attn.out_proj.weight"].T + P["transformer.layers.0.self_attn.out_proj.bias"]
+    x1 = x0 + y * masks[2].view(B, T, D)
+    u2 = F.layer_norm(x1, (D,), P["transformer.layers.0.norm2.weight"], P["transformer.layers.0.norm2.bias"])
+    z = u2 @ P["transformer.layers.0.linear1.weight"].T + P["transformer.layers.0.linear1.bias"]
+    m = F.gelu(z) * masks[3].view(B, T, -1)
+    y2 = m @ P["transformer.layers.0.linear2.weight"].T + P["transformer.layers.0.linear2.bias"]
+    x2 = x1 + y2 * masks[4].view(B, T, D)
+    h = F.layer_norm(x2, (D,), P["layer_norm.weight"], P["layer_norm.bias"])
+    return (h @ P["output_layer.weight"].T + P["output_layer.bias"]).squeeze(-1)
+
+
+def test_head_train_step_with_dropout_matches_autograd():
+    """train()-mode step: init_dropout on the encoder output + the layer's dropout at its four sites, against
+    torch.autograd on a hand-written head that applies the SAME masks (rebuilt on the host from the seed)"""
+    B, T, lens, pw, p0, pl, seed = 2, 222, [222, 131], 1.3, 0.1, 0.1, 77
+    eng, head, hidden, mask, target = _setup(B, T, lens, 9)
+    trainer = HeadTrainer(eng, head, init_dropout=p0, layer_dropout=pl, seed=seed)
+    logits = torch.empty(B, T, device="cuda")
+    loss = trainer.step_hidden(hidden, lens, target, pw, logits_out=logits)
+    assert trainer.seed == seed + 1
+    torch.cuda.synchronize()
+    heads, D, Fd = 8, 1024, head["transformer.layers.0.linear1.weight"].shape[0]
+    sizes = [B * T * D, B * heads * T * T, B * T * D, B * T * Fd, B * T * D]
+    masks = [dropout_mask(p0 if i == 0 else pl, seed, i, sz, "cuda") for i, sz in enumerate(sizes)]
+    for i, mk in enumerate(masks):     # the hash really drops about p of the elements
+        frac = float((mk == 0).float().mean())
+        assert abs(frac - (p0 if i == 0 else pl)) < 0.01, (i, frac)
+    params = {k: v.cuda().clone().requires_grad_(True) for k, v in head.items()}
+    out = _manual_head(params, hidden, mask, heads, masks)
+    lpp = torch.nn.functional.binary_cross_entropy_with_logits(out, target, pos_weight=torch.tensor(pw).cuda(), reduction="none")
+    ref_loss = lpp.masked_fill(~mask, 0.0).sum(dim=1).mean()
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 5e-3, (loss.item(), ref_loss.item())
+    assert (logits - out.detach().masked_fill(~mask, 0.0)).abs().max().item() < 5e-2
+    worst = {k: rel(trainer.params[k].grad, p.grad) for k, p in params.items()}
+    print("TRAIN dropout grad rel. errors:", {k: round(v, 4) for k, v in worst.items()})
+    assert max(worst.values()) < 4e-2, worst
+    # the masks matter (a different seed gives a different loss) and the step is reproducible from its seed
+    t2 = HeadTrainer(eng, head, init_dropout=p0, layer_dropout=pl, seed=seed)
+    l2 = t2.step_hidden(hidden, lens, target, pw)
+    for k in params:
+        assert torch.equal(t2.params[k].grad, trainer.params[k].grad), k
+    l3 = t2.step_hidden(hidden, lens, target, pw)          # seed advanced: other masks
+    assert l2.item() == loss.item() and l3.item() != loss.item()
     eng.close()
 
 

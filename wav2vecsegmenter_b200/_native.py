@@ -14,7 +14,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("W2VSEG_LIB") or Path(__file__).resolve().parent / "csrc" / "libw2vseg.so")
 
 _lib = None
-ABI_VERSION = 3   # W2VSEG_ABI_VERSION of include/w2vseg.h this binding was written against
+ABI_VERSION = 4   # W2VSEG_ABI_VERSION of include/w2vseg.h this binding was written against
 
 
 class W2VSegError(RuntimeError):
@@ -67,12 +67,14 @@ SIGNATURES = {
     "w2vseg_workspace_bytes": (_SZ, [_P, _I32, _I64]),
     "w2vseg_encode": (_I32, [_P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "w2vseg_head": (_I32, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _SZ, _P]),
-    "w2vseg_attention_train": (_I32, [_P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P, _P]),
-    "w2vseg_attention_bwd": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),
+    "w2vseg_attention_train": (_I32, [_P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P, C.c_float, C.c_uint32, _P]),
+    "w2vseg_attention_bwd": (_I32, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, C.c_float, _P, C.c_float, C.c_uint32,
+                             _P]),
     "w2vseg_head_grad_floats": (_I64, [_P]),
     "w2vseg_head_grad_offset": (_I64, [_P, C.c_char_p, C.POINTER(_I64)]),
     "w2vseg_head_train_workspace_bytes": (_SZ, [_P, _I32, _I32]),
-    "w2vseg_head_train_step": (_I32, [_P, _P, _I64, _I32, _P, _P, C.c_float, _I32, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    "w2vseg_head_train_step": (_I32, [_P, _P, _I64, _I32, _P, _P, C.c_float, _I32, _P, _P, _P, _SZ, C.c_float, C.c_float,
+                               C.c_uint32, _P, _SZ, _P]),
     "w2vseg_calibrate": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _SZ, _P]),
     "w2vseg_correct_bias": (_I32, [_P, C.c_char_p, _P, _I64, _P]),
     "w2vseg_sfc_forward": (_I32, [_P, _P, _I64, _P, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),

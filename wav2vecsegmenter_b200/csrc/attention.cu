@@ -19,11 +19,13 @@ namespace w2v {
 
 namespace {
 
-template <int DH>
+// DROP (training forward only): the attention weights that multiply V are masked and rescaled, the row sum
+// (and the log-sum-exp the backward uses) stays that of the full softmax — torch's dropout(softmax(S)) V.
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
                  const int* __restrict__ kv_len, float scale_log2,
-                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, DropSite drop) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   constexpr int TILE_BYTES = ATT_BKV * DH * 2;
   const uint32_t sQ = smem_u32(att_smem);
@@ -125,12 +127,19 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
     uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float p0 = exp2f(fmaf(s[i][0], scale_log2, -moff[0]));
-      const float p1 = exp2f(fmaf(s[i][1], scale_log2, -moff[0]));
-      const float p2 = exp2f(fmaf(s[i][2], scale_log2, -moff[1]));
-      const float p3 = exp2f(fmaf(s[i][3], scale_log2, -moff[1]));
+      float p0 = exp2f(fmaf(s[i][0], scale_log2, -moff[0]));
+      float p1 = exp2f(fmaf(s[i][1], scale_log2, -moff[0]));
+      float p2 = exp2f(fmaf(s[i][2], scale_log2, -moff[1]));
+      float p3 = exp2f(fmaf(s[i][3], scale_log2, -moff[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
+      if (DROP) {
+        const uint32_t q_lo = (uint32_t)(q0 + warp * 16 + (lane >> 2));
+        const uint32_t e0 = ((uint32_t)(b * heads + head) * (uint32_t)R + q_lo) * (uint32_t)R + (uint32_t)(key0 + i * 8);
+        const uint32_t e1 = e0 + 8u * (uint32_t)R;
+        p0 *= drop_factor(drop, e0); p1 *= drop_factor(drop, e0 + 1);
+        p2 *= drop_factor(drop, e1); p3 *= drop_factor(drop, e1 + 1);
+      }
       pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16x2(p0, p1);
       pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(p2, p3);
     }
@@ -210,7 +219,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int R, int heads,
 }  // namespace
 
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
-                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s, float* lse) {
+                     const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s, float* lse,
+                     const DropSite* drop) {
   if (B <= 0 || R <= 0) return 0;
   W2V_REQUIRE(head_dim == 64 || head_dim == 128, "attention: head_dim %d unsupported (64 / 128)",
               head_dim);
@@ -218,14 +228,20 @@ int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head
   dim3 grid((R + ATT_BQ - 1) / ATT_BQ, heads, B);
   const int smem = 5 * ATT_BKV * head_dim * 2;
   ProfScope ps(s, head_dim == 64 ? "attention_d64" : "attention_d128");
+  const bool dropping = drop != nullptr && drop->thresh != 0;
+  const DropSite d = dropping ? *drop : DropSite{0, 0, 1.f};
   if (head_dim == 64) {
-    attention_kernel<64><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse);
+    if (dropping) attention_kernel<64, true><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse, d);
+    else attention_kernel<64, false><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse, d);
   } else {
     W2V_ONCE_BEGIN
-      W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>,
+      W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     W2V_ONCE_END
-    attention_kernel<128><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse);
+    if (dropping) attention_kernel<128, true><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse, d);
+    else attention_kernel<128, false><<<grid, ATT_THREADS, smem, s>>>(qkv, R, heads, kv_len, scale_log2, ctx, lse, d);
   }
   W2V_CHECK_LAUNCH();
   return 0;

@@ -8,6 +8,8 @@
 //   dP  = dO V^T
 //   dS  = P * (dP - delta) * scale                      delta_i = sum_d dO_id O_id
 //   dQ  = dS K          dK = dS^T Q
+// With dropout on the attention weights (mask M in {0, 1/(1-p)}, regenerated from dropout.cuh's hash):
+//   O = (P . M) V   ->   dV = (P . M)^T dO,   dP = (dO V^T) . M,   delta unchanged (sum_j P_ij dP_ij = dO_i . O_i).
 //
 // Three launches of one kernel template, each accumulating ONE gradient in registers (dQ per query tile with
 // the key tiles streaming; dV and dK per key tile with the query tiles streaming) — no atomics, deterministic,
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
                      const float* __restrict__ lse, const float* __restrict__ delta, int R, int heads,
                      const int* __restrict__ kv_len, float scale, float scale_log2,
-                     __nv_bfloat16* __restrict__ dqkv) {
+                     __nv_bfloat16* __restrict__ dqkv, DropSite drop) {
   extern __shared__ __align__(128) uint8_t bwd_smem[];
   constexpr int TILE_BYTES = 64 * DH * 2;
   constexpr int ONT = DH / 8;
@@ -205,8 +207,21 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
         s[i][e] = ok ? exp2f(fmaf(s[i][e], scale_log2, -lq)) : 0.f;
       }
     }
+    // dropout factor of element (i, e) of this thread's fragment: rows = owned rows, columns = streamed rows
+    const uint32_t bh = (uint32_t)(b * heads + head) * (uint32_t)R;
+    auto mask_of = [&](int i, int e) -> float {
+      const uint32_t own = (uint32_t)(row_lo + 8 * (e >> 1)), str = (uint32_t)(col0 + 8 * i + (e & 1));
+      const uint32_t q = MODE == BWD_DQ ? own : str, k = MODE == BWD_DQ ? str : own;
+      return drop_factor(drop, (bh + q) * (uint32_t)R + k);
+    };
     uint32_t pf[4][4];
     if (MODE == BWD_DV) {
+      if (drop.thresh != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[i][e] *= mask_of(i, e);
+      }
       pack_frags(s, pf);
       mma_rows_as_k<DH>(acc, pf, tB, lane);  // dV += P^T dO
     } else {
@@ -215,6 +230,12 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       load_a_frags<DH>(sFixB, warp, lane, fb);
       float dp[8][4];
       mma_rows_as_n<DH>(dp, fb, tB, lane);
+      if (drop.thresh != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dp[i][e] *= mask_of(i, e);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -261,7 +282,8 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 template <int DH, int MODE>
 int launch_mode(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const float* lse, const float* delta, int B,
-                int R, int heads, const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, cudaStream_t s) {
+                int R, int heads, const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, const DropSite& drop,
+                cudaStream_t s) {
   const int smem = 6 * 64 * DH * 2 + 4 * 64 * (int)sizeof(float);
   W2V_ONCE_BEGIN
   W2V_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -269,7 +291,7 @@ int launch_mode(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const float
   dim3 grid((R + 63) / 64, heads, B);
   ProfScope ps(s, MODE == BWD_DQ ? "attention_bwd_dq" : MODE == BWD_DV ? "attention_bwd_dv" : "attention_bwd_dk");
   attention_bwd_kernel<DH, MODE><<<grid, ATT_THREADS, smem, s>>>(qkv, dctx, lse, delta, R, heads, kv_len, scale,
-                                                                  scale * 1.4426950408889634f, dqkv);
+                                                                  scale * 1.4426950408889634f, dqkv, drop);
   W2V_CHECK_LAUNCH();
   return 0;
 }
@@ -278,20 +300,21 @@ int launch_mode(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, const float
 
 int attention_bwd_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
                          const float* lse, float* delta, int B, int R, int heads, int head_dim,
-                         const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, cudaStream_t s) {
+                         const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, const DropSite& drop,
+                         cudaStream_t s) {
   if (B <= 0 || R <= 0) return 0;
   W2V_REQUIRE(head_dim == 64 || head_dim == 128, "attention_bwd: head_dim %d unsupported (64 / 128)", head_dim);
   const long long warps = (long long)B * R * heads;
   attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(ctx, dctx, B, R, heads, head_dim, delta);
   W2V_CHECK_LAUNCH();
   if (head_dim == 64) {
-    W2V_TRY((launch_mode<64, BWD_DQ>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
-    W2V_TRY((launch_mode<64, BWD_DV>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
-    W2V_TRY((launch_mode<64, BWD_DK>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
+    W2V_TRY((launch_mode<64, BWD_DQ>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
+    W2V_TRY((launch_mode<64, BWD_DV>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
+    W2V_TRY((launch_mode<64, BWD_DK>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
   } else {
-    W2V_TRY((launch_mode<128, BWD_DQ>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
-    W2V_TRY((launch_mode<128, BWD_DV>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
-    W2V_TRY((launch_mode<128, BWD_DK>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, s)));
+    W2V_TRY((launch_mode<128, BWD_DQ>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
+    W2V_TRY((launch_mode<128, BWD_DV>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
+    W2V_TRY((launch_mode<128, BWD_DK>(qkv, dctx, lse, delta, B, R, heads, kv_len, scale, dqkv, drop, s)));
   }
   return 0;
 }

@@ -917,18 +917,24 @@ int32_t w2vseg_attention_mma(const void* qkv, int32_t B, int32_t R, int32_t head
 }
 
 int32_t w2vseg_attention_train(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
-                               const int32_t* kv_len, float scale, void* ctx, float* lse, void* stream) {
+                               const int32_t* kv_len, float scale, void* ctx, float* lse, float dropout,
+                               uint32_t seed, void* stream) {
   W2V_REQUIRE(qkv && kv_len && ctx && lse, "attention_train: null argument");
+  W2V_REQUIRE(dropout >= 0.f && dropout < 1.f, "attention_train: dropout %g outside [0, 1)", (double)dropout);
+  const DropSite d = make_drop_site(dropout, seed, 1);
   return attention_launch((const bf16*)qkv, B, R, heads, head_dim, kv_len, scale, (bf16*)ctx,
-                          (cudaStream_t)stream, lse);
+                          (cudaStream_t)stream, lse, &d);
 }
 
 int32_t w2vseg_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse,
                              float* delta_scratch, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
-                             const int32_t* kv_len, float scale, void* dqkv, void* stream) {
+                             const int32_t* kv_len, float scale, void* dqkv, float dropout, uint32_t seed,
+                             void* stream) {
   W2V_REQUIRE(qkv && ctx && dctx && lse && delta_scratch && kv_len && dqkv, "attention_bwd: null argument");
+  W2V_REQUIRE(dropout >= 0.f && dropout < 1.f, "attention_bwd: dropout %g outside [0, 1)", (double)dropout);
   return attention_bwd_launch((const bf16*)qkv, (const bf16*)ctx, (const bf16*)dctx, lse, delta_scratch, B, R,
-                              heads, head_dim, kv_len, scale, (bf16*)dqkv, (cudaStream_t)stream);
+                              heads, head_dim, kv_len, scale, (bf16*)dqkv, make_drop_site(dropout, seed, 1),
+                              (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -1044,8 +1050,11 @@ size_t w2vseg_head_train_workspace_bytes(const w2vseg_handle* h, int32_t B, int3
 int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t batch_stride, int32_t T,
                                const int32_t* out_len, const float* target, float pos_weight, int32_t B,
                                float* loss_out, float* logits_out, float* grads, size_t grads_floats,
+                               float init_dropout, float layer_dropout, uint32_t seed,
                                void* workspace, size_t workspace_bytes, void* stream) {
   W2V_TRY(check_ready(h));
+  W2V_REQUIRE(init_dropout >= 0.f && init_dropout < 1.f && layer_dropout >= 0.f && layer_dropout < 1.f,
+              "head_train_step: dropout (%g, %g) outside [0, 1)", (double)init_dropout, (double)layer_dropout);
   W2V_REQUIRE(hidden && out_len && target && loss_out && grads && workspace, "head_train_step: null argument");
   W2V_REQUIRE(B > 0 && T > 0 && batch_stride >= (int64_t)T * h->D && batch_stride % 4 == 0,
               "head_train_step: bad shape (B=%d, T=%d, batch_stride=%lld)", B, T, (long long)batch_stride);
@@ -1069,18 +1078,37 @@ int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t ba
   const int64_t M = (int64_t)B * T;
   const float scale = 1.0f / sqrtf((float)hd);
 
-  // ---------------- forward, keeping what the backward needs (dropout: not applied, see w2vseg.h)
-  W2V_TRY(gather_rows_launch(hidden, batch_stride, B, T, D, w.x0, st));
+  // Dropout sites of the head in train() mode (lib/models.py:291-319): 0 init_dropout on the encoder output,
+  // 1 attention weights, 2 after the attention block (dropout1), 3 inside the FFN, 4 after the FFN (dropout2).
+  // Masks are regenerated from (seed, site, element index) wherever they are needed (dropout.cuh).
+  const DropSite d0 = make_drop_site(init_dropout, seed, 0), d1 = make_drop_site(layer_dropout, seed, 1),
+                 d2 = make_drop_site(layer_dropout, seed, 2), d3 = make_drop_site(layer_dropout, seed, 3),
+                 d4 = make_drop_site(layer_dropout, seed, 4);
+  const bool drop_layer = layer_dropout > 0.f;
+
+  // ---------------- forward, keeping what the backward needs
+  if (init_dropout > 0.f) W2V_TRY(gather_dropout_launch(hidden, batch_stride, B, T, D, w.x0, d0, st));
+  else W2V_TRY(gather_rows_launch(hidden, batch_stride, B, T, D, w.x0, st));
   W2V_TRY(layernorm_launch(w.x0, true, M, D, H.ln1.g, H.ln1.b, c.ln_eps, 0, w.u1, st));
   W2V_TRY(gemm_plain(w.u1, M, D, H.win, 3 * D, H.bin, w.qkv, 3 * D, false, nullptr, "train.fwd", st));
-  W2V_TRY(attention_launch(w.qkv, B, T, c.head_heads, hd, out_len, scale, w.ctx, st, w.lse));
-  W2V_TRY(copy_f32_launch(w.x0, w.x1, M * D, st));
-  W2V_TRY(gemm_plain(w.ctx, M, D, H.wo, D, H.bo, w.x1, D, true, w.x1, "train.fwd", st));
+  W2V_TRY(attention_launch(w.qkv, B, T, c.head_heads, hd, out_len, scale, w.ctx, st, w.lse, &d1));
+  if (drop_layer) {     // branch output to a scratch (dx1 is free until the backward), then x1 = x0 + dropout(branch)
+    W2V_TRY(gemm_plain(w.ctx, M, D, H.wo, D, H.bo, w.dx1, D, true, nullptr, "train.fwd", st));
+    W2V_TRY(resid_dropout_launch(w.x0, w.dx1, w.x1, M * D, d2, st));
+  } else {
+    W2V_TRY(copy_f32_launch(w.x0, w.x1, M * D, st));
+    W2V_TRY(gemm_plain(w.ctx, M, D, H.wo, D, H.bo, w.x1, D, true, w.x1, "train.fwd", st));
+  }
   W2V_TRY(layernorm_launch(w.x1, true, M, D, H.ln2.g, H.ln2.b, c.ln_eps, 0, w.u2, st));
   W2V_TRY(gemm_plain(w.u2, M, D, H.w1, F, H.b1, w.z1, F, false, nullptr, "train.fwd", st));
-  W2V_TRY(gelu_fwd_launch(w.z1, w.m, M * F, st));
-  W2V_TRY(copy_f32_launch(w.x1, w.x2, M * D, st));
-  W2V_TRY(gemm_plain(w.m, M, F, H.w2, D, H.b2, w.x2, D, true, w.x2, "train.fwd", st));
+  W2V_TRY(gelu_fwd_launch(w.z1, w.m, M * F, d3, st));
+  if (drop_layer) {
+    W2V_TRY(gemm_plain(w.m, M, F, H.w2, D, H.b2, w.dx2, D, true, nullptr, "train.fwd", st));
+    W2V_TRY(resid_dropout_launch(w.x1, w.dx2, w.x2, M * D, d4, st));
+  } else {
+    W2V_TRY(copy_f32_launch(w.x1, w.x2, M * D, st));
+    W2V_TRY(gemm_plain(w.m, M, F, H.w2, D, H.b2, w.x2, D, true, w.x2, "train.fwd", st));
+  }
 
   // ---------------- loss + backward
   W2V_TRY(head_loss_backward_launch(w.x2, B, T, H.lnf.g, H.lnf.b, c.ln_eps, H.wout, H.bout, out_len, target,
@@ -1088,23 +1116,33 @@ int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t ba
   W2V_TRY(final_param_grads_launch(w.dlogit, w.x2, w.st2, M, D, H.lnf.g, H.lnf.b, H.wout, w.red, kRedFloats, w.tmpA,
                                    w.tmpS, G("head.out.weight"), G("head.ln_f.weight"), G("head.ln_f.bias"),
                                    G("head.out.bias"), st));
-  // FFN: x2 = x1 + gelu(u2 W1^T + b1) W2^T + b2
-  W2V_TRY(colsum_launch(w.dx2, false, D, M, D, w.red, kRedFloats, G("head.ff2.bias"), st));
+  // FFN: x2 = x1 + drop4(drop3(gelu(u2 W1^T + b1)) W2^T + b2); the branch sees the masked gradient (dx2b)
+  if (drop_layer) {
+    W2V_TRY(mask_cast_launch(w.dx2, w.dx2b, M * D, d4, st));
+    W2V_TRY(colsum_launch(w.dx2b, true, D, M, D, w.red, kRedFloats, G("head.ff2.bias"), st));
+  } else {
+    W2V_TRY(colsum_launch(w.dx2, false, D, M, D, w.red, kRedFloats, G("head.ff2.bias"), st));
+  }
   W2V_TRY(wgrad(w.dx2b, D, D, w.m, F, F, M, w, G("head.ff2.weight"), st));
   W2V_TRY(dgrad(w.dx2b, M, D, H.w2, F, F, w, w.dm, st));
-  W2V_TRY(gelu_bwd_launch(w.z1, w.dm, w.dz1, M * F, st));
+  W2V_TRY(gelu_bwd_launch(w.z1, w.dm, w.dz1, M * F, d3, st));
   W2V_TRY(colsum_launch(w.dz1, true, F, M, F, w.red, kRedFloats, G("head.ff1.bias"), st));
   W2V_TRY(wgrad(w.dz1, F, F, w.u2, D, D, M, w, G("head.ff1.weight"), st));
   W2V_TRY(dgrad(w.dz1, M, F, H.w1, D, D, w, w.du2, st));
   // LN2: dx1 = dx2 + LN2'(du2)
   W2V_TRY(layernorm_bwd_launch(w.x1, w.du2, M, H.ln2.g, c.ln_eps, w.dx2, w.dx1, w.dx1b, w.st1, st));
   W2V_TRY(ln_param_grads_launch(w.du2, w.x1, w.st1, M, D, w.red, kRedFloats, G("head.ln2.weight"), G("head.ln2.bias"), st));
-  // attention output projection: x1 = x0 + ctx Wo^T + bo
-  W2V_TRY(colsum_launch(w.dx1, false, D, M, D, w.red, kRedFloats, G("head.o.bias"), st));
+  // attention output projection: x1 = x0 + drop2(ctx Wo^T + bo)
+  if (drop_layer) {
+    W2V_TRY(mask_cast_launch(w.dx1, w.dx1b, M * D, d2, st));
+    W2V_TRY(colsum_launch(w.dx1b, true, D, M, D, w.red, kRedFloats, G("head.o.bias"), st));
+  } else {
+    W2V_TRY(colsum_launch(w.dx1, false, D, M, D, w.red, kRedFloats, G("head.o.bias"), st));
+  }
   W2V_TRY(wgrad(w.dx1b, D, D, w.ctx, D, D, M, w, G("head.o.weight"), st));
   W2V_TRY(dgrad(w.dx1b, M, D, H.wo, D, D, w, w.dctx, st));
   // attention
-  W2V_TRY(attention_bwd_launch(w.qkv, w.ctx, w.dctx, w.lse, w.delta, B, T, c.head_heads, hd, out_len, scale, w.dqkv, st));
+  W2V_TRY(attention_bwd_launch(w.qkv, w.ctx, w.dctx, w.lse, w.delta, B, T, c.head_heads, hd, out_len, scale, w.dqkv, d1, st));
   // input projection: qkv = u1 Win^T + bin
   W2V_TRY(colsum_launch(w.dqkv, true, 3 * D, M, 3 * D, w.red, kRedFloats, G("head.in_proj.bias"), st));
   W2V_TRY(wgrad(w.dqkv, 3 * D, 3 * D, w.u1, D, D, M, w, G("head.in_proj.weight"), st));

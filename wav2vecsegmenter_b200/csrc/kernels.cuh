@@ -2,6 +2,7 @@
 // attention kernel (attention.cu). All take device pointers and a stream; all return 0 / W2VSEG_ERR_*.
 #pragma once
 #include "common.h"
+#include "dropout.cuh"
 
 namespace w2v {
 
@@ -64,14 +65,16 @@ int head_final_launch(const float* y, int B, int R, int C, const float* gamma, c
 
 // fused non-causal attention, key-length masked (HF:500-549; torch MHA in lib/models.py:291-300)
 // lse (optional, fp32 [B, heads, R]): per-row log-sum-exp in the log2 domain, for attention_bwd_launch
+// drop (optional, training only): dropout on the attention weights, mask index ((b*heads + h)*R + q)*R + k
 int attention_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,
                      const int32_t* kv_len, float scale, __nv_bfloat16* ctx, cudaStream_t s,
-                     float* lse = nullptr);
+                     float* lse = nullptr, const DropSite* drop = nullptr);
 // backward of the same attention (head training step, attention_bwd.cu): dqkv bf16 [B*R, 3*D] (dQ | dK | dV)
 // from dctx bf16 [B*R, D], the forward's qkv / ctx and lse. delta: fp32 [B, heads, R] scratch.
 int attention_bwd_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* ctx, const __nv_bfloat16* dctx,
                          const float* lse, float* delta, int B, int R, int heads, int head_dim,
-                         const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, cudaStream_t s);
+                         const int32_t* kv_len, float scale, __nv_bfloat16* dqkv, const DropSite& drop,
+                         cudaStream_t s);
 
 // same contract, tcgen05 / TMEM / TMA implementation (attention_tc.cu) — the product path
 int attention_tc_launch(const __nv_bfloat16* qkv, int B, int R, int heads, int head_dim,

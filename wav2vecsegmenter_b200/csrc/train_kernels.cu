@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "train_kernels.cuh"
+#include "dropout.cuh"
 
 namespace w2v {
 
@@ -239,25 +240,66 @@ sum_rows_kernel(const float* __restrict__ v, long long n, float* __restrict__ ou
 }
 
 // ---- GELU on stored pre-activations (erf form, lib/models.py:296 activation="gelu") -----------------------
+// element index of the dropout mask = flat index into the [rows, cols] matrix
 __global__ void __launch_bounds__(256)
-gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ out, long long n2) {
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ out, long long n2, DropSite d) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n2) return;
   const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(z)[i]);
-  reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(0.5f * v.x * (1.f + erff(v.x * 0.70710678f)),
-                                                   0.5f * v.y * (1.f + erff(v.y * 0.70710678f)));
+  float a = 0.5f * v.x * (1.f + erff(v.x * 0.70710678f)), b = 0.5f * v.y * (1.f + erff(v.y * 0.70710678f));
+  if (d.thresh != 0) { a *= drop_factor(d, (uint32_t)(2 * i)); b *= drop_factor(d, (uint32_t)(2 * i + 1)); }
+  reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(a, b);
 }
 __device__ __forceinline__ float gelu_grad(float x) {   // Phi(x) + x phi(x)
   return 0.5f * (1.f + erff(x * 0.70710678f)) + x * 0.3989422804f * expf(-0.5f * x * x);
 }
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dm,
-                __nv_bfloat16* __restrict__ dz, long long n2) {
+                __nv_bfloat16* __restrict__ dz, long long n2, DropSite d) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n2) return;
   const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(z)[i]);
-  const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(dm)[i]);
+  float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(dm)[i]);
+  if (d.thresh != 0) { g.x *= drop_factor(d, (uint32_t)(2 * i)); g.y *= drop_factor(d, (uint32_t)(2 * i + 1)); }
   reinterpret_cast<uint32_t*>(dz)[i] = pack_bf16x2(g.x * gelu_grad(v.x), g.y * gelu_grad(v.y));
+}
+
+// x_out = x_in + dropout(y)  (residual branch with the TransformerEncoderLayer's dropout1 / dropout2), fp32
+__global__ void __launch_bounds__(256)
+resid_dropout_kernel(const float* __restrict__ x_in, const float* __restrict__ y, float* __restrict__ x_out,
+                     long long n4, DropSite d) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = reinterpret_cast<const float4*>(x_in)[i];
+  const float4 b = reinterpret_cast<const float4*>(y)[i];
+  const uint32_t e = (uint32_t)(4 * i);
+  reinterpret_cast<float4*>(x_out)[i] =
+      make_float4(fmaf(b.x, drop_factor(d, e), a.x), fmaf(b.y, drop_factor(d, e + 1), a.y),
+                  fmaf(b.z, drop_factor(d, e + 2), a.z), fmaf(b.w, drop_factor(d, e + 3), a.w));
+}
+// dst_bf16 = dropout-mask(src) (the gradient entering a dropped branch), or a plain gather + dropout in fp32
+__global__ void __launch_bounds__(256)
+mask_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, DropSite d) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = reinterpret_cast<const float4*>(src)[i];
+  const uint32_t e = (uint32_t)(4 * i);
+  uint2 u;
+  u.x = pack_bf16x2(a.x * drop_factor(d, e), a.y * drop_factor(d, e + 1));
+  u.y = pack_bf16x2(a.z * drop_factor(d, e + 2), a.w * drop_factor(d, e + 3));
+  reinterpret_cast<uint2*>(dst)[i] = u;
+}
+__global__ void __launch_bounds__(256)
+gather_dropout_kernel(const float* __restrict__ src, long long batch_stride, int T, int C, float* __restrict__ dst,
+                      long long n4, DropSite d) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const long long per_b = (long long)T * C / 4;
+  const long long b = i / per_b, r = i - b * per_b;
+  const float4 a = *reinterpret_cast<const float4*>(src + b * batch_stride + r * 4);
+  const uint32_t e = (uint32_t)(4 * i);
+  reinterpret_cast<float4*>(dst)[i] = make_float4(a.x * drop_factor(d, e), a.y * drop_factor(d, e + 1),
+                                                   a.z * drop_factor(d, e + 2), a.w * drop_factor(d, e + 3));
 }
 
 // ---- bf16 transpose with zero padding: dst[c, r] = src[r, c] for r < rows, 0 for rows <= r < rows_pad ------
@@ -350,17 +392,41 @@ int final_param_grads_launch(const float* dlogit, const float* x2, const float2*
   return 0;
 }
 
-int gelu_fwd_launch(const __nv_bfloat16* z, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
+int gelu_fwd_launch(const __nv_bfloat16* z, __nv_bfloat16* out, int64_t n, const DropSite& d, cudaStream_t s) {
   if (n <= 0) return 0;
   ProfScope ps(s, "train.gelu");
-  gelu_fwd_kernel<<<blocks_for_t(n / 2, 256), 256, 0, s>>>(z, out, n / 2);
+  gelu_fwd_kernel<<<blocks_for_t(n / 2, 256), 256, 0, s>>>(z, out, n / 2, d);
   W2V_CHECK_LAUNCH();
   return 0;
 }
-int gelu_bwd_launch(const __nv_bfloat16* z, const __nv_bfloat16* dm, __nv_bfloat16* dz, int64_t n, cudaStream_t s) {
+int gelu_bwd_launch(const __nv_bfloat16* z, const __nv_bfloat16* dm, __nv_bfloat16* dz, int64_t n, const DropSite& d,
+                    cudaStream_t s) {
   if (n <= 0) return 0;
   ProfScope ps(s, "train.gelu_bwd");
-  gelu_bwd_kernel<<<blocks_for_t(n / 2, 256), 256, 0, s>>>(z, dm, dz, n / 2);
+  gelu_bwd_kernel<<<blocks_for_t(n / 2, 256), 256, 0, s>>>(z, dm, dz, n / 2, d);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+int resid_dropout_launch(const float* x_in, const float* y, float* x_out, int64_t n, const DropSite& d, cudaStream_t s) {
+  if (n <= 0) return 0;
+  ProfScope ps(s, "train.dropout");
+  resid_dropout_kernel<<<blocks_for_t(n / 4, 256), 256, 0, s>>>(x_in, y, x_out, n / 4, d);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+int mask_cast_launch(const float* src, __nv_bfloat16* dst, int64_t n, const DropSite& d, cudaStream_t s) {
+  if (n <= 0) return 0;
+  ProfScope ps(s, "train.dropout");
+  mask_cast_kernel<<<blocks_for_t(n / 4, 256), 256, 0, s>>>(src, dst, n / 4, d);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
+int gather_dropout_launch(const float* src, int64_t batch_stride, int B, int T, int C, float* dst, const DropSite& d,
+                          cudaStream_t s) {
+  const long long n4 = (long long)B * T * C / 4;
+  if (n4 <= 0) return 0;
+  ProfScope ps(s, "train.dropout");
+  gather_dropout_kernel<<<blocks_for_t(n4, 256), 256, 0, s>>>(src, batch_stride, T, C, dst, n4, d);
   W2V_CHECK_LAUNCH();
   return 0;
 }

@@ -2,6 +2,7 @@
 // 0 / W2VSEG_ERR_* return codes. Reference: train.py:381-480 (loss, backward) around lib/models.py:279-319.
 #pragma once
 #include "common.h"
+#include "dropout.cuh"
 
 namespace w2v {
 
@@ -25,8 +26,17 @@ int final_param_grads_launch(const float* dlogit, const float* x2, const float2*
                              const float* gamma, const float* beta, const float* w_out, float* scratch,
                              size_t scratch_floats, float* tmpA, float* tmpS, float* d_w, float* d_gamma,
                              float* d_beta, float* d_b, cudaStream_t s);
-int gelu_fwd_launch(const __nv_bfloat16* z, __nv_bfloat16* out, int64_t n, cudaStream_t s);
-int gelu_bwd_launch(const __nv_bfloat16* z, const __nv_bfloat16* dm, __nv_bfloat16* dz, int64_t n, cudaStream_t s);
+// out = dropout(gelu(z)) / dz = dm * mask * gelu'(z); the mask index is the flat element index (d.thresh 0: none)
+int gelu_fwd_launch(const __nv_bfloat16* z, __nv_bfloat16* out, int64_t n, const DropSite& d, cudaStream_t s);
+int gelu_bwd_launch(const __nv_bfloat16* z, const __nv_bfloat16* dm, __nv_bfloat16* dz, int64_t n, const DropSite& d,
+                    cudaStream_t s);
+// x_out = x_in + dropout(y), fp32 [n]
+int resid_dropout_launch(const float* x_in, const float* y, float* x_out, int64_t n, const DropSite& d, cudaStream_t s);
+// dst (bf16) = src (fp32) * dropout mask: the gradient entering a dropped residual branch
+int mask_cast_launch(const float* src, __nv_bfloat16* dst, int64_t n, const DropSite& d, cudaStream_t s);
+// gather_rows + dropout (init_dropout on the encoder output)
+int gather_dropout_launch(const float* src, int64_t batch_stride, int B, int T, int C, float* dst, const DropSite& d,
+                          cudaStream_t s);
 // dst[c, r] = src[r, c] (r < rows), zero for rows <= r < rows_pad; dst leading dimension rows_pad
 int transpose_bf16_launch(const __nv_bfloat16* src, int64_t ld_src, int64_t rows, int cols, __nv_bfloat16* dst,
                           int64_t rows_pad, cudaStream_t s);

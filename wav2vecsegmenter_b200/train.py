@@ -3,6 +3,12 @@ train.py:381-480 around lib/models.py:214-235, 279-319). The encoder forward is 
 (no gradient), the head forward / loss / backward is `w2vseg_head_train_step`; the optimiser is the caller's
 (torch.optim on fp32 master parameters kept here), and after every step the head parameters are re-uploaded
 into the handle (bf16 matrices, fp32 vectors).
+
+Dropout: the reference trains the head in train() mode — `init_dropout` (conf/task/shas.yaml:14, 0.1) on the encoder
+output (lib/models.py:302,312) and the TransformerEncoderLayer's default 0.1 at its four sites. `HeadTrainer(...,
+init_dropout=0.1, layer_dropout=0.1)` applies both with counter-hash masks (csrc/dropout.cuh); `dropout_masks()`
+below rebuilds the same masks on the host side for the parity test. The defaults (0, 0) give the deterministic
+eval-mode gradient.
 """
 from __future__ import annotations
 
@@ -20,7 +26,10 @@ class HeadTrainer:
         loss = trainer.step(audio, sample_len, norm_len, out_len, target, pos_weight); opt.step(); trainer.sync()
     """
 
-    def __init__(self, engine: SFCEngine, head_state: dict):
+    def __init__(self, engine: SFCEngine, head_state: dict, init_dropout: float = 0.0, layer_dropout: float = 0.0,
+                 seed: int = 0):
+        self.init_dropout, self.layer_dropout = float(init_dropout), float(layer_dropout)
+        self.seed = int(seed) & 0xFFFFFFFF       # seed of the NEXT step; advanced by every step
         self.engine = engine
         self.lib = engine.lib
         self.params: dict[str, torch.nn.Parameter] = {}
@@ -77,8 +86,10 @@ class HeadTrainer:
         nat.check(self.lib.w2vseg_head_train_step(eng._h, hidden.data_ptr(), hidden.stride(0), T, ol.data_ptr(),
                                                   tg.data_ptr(), float(pos_weight), B, self._loss.data_ptr(),
                                                   nat.ptr(logits_out), self._grads.data_ptr(), self._grads.numel(),
+                                                  self.init_dropout, self.layer_dropout, self.seed,
                                                   self._ws.data_ptr(), self._ws.numel(), eng._stream()),
                   "w2vseg_head_train_step")
+        self.seed = (self.seed + 1) & 0xFFFFFFFF
         for k, p in self.params.items():
             g = self._views[k]
             p.grad = g.clone() if p.grad is None else p.grad + g
@@ -99,3 +110,25 @@ class HeadTrainer:
             ol = torch.clamp(ol, max=Tt - 1)
             Tt -= 1
         return self.step_hidden(hidden[:, :Tt], ol, target, pos_weight)
+
+
+def _lowbias32(x: torch.Tensor) -> torch.Tensor:
+    """the integer hash of csrc/dropout.cuh on int64 tensors holding uint32 values"""
+    m = 0xFFFFFFFF
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & m
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & m
+    return x ^ (x >> 16)
+
+
+def dropout_mask(p: float, seed: int, site: int, numel: int, device="cpu") -> torch.Tensor:
+    """factor (0 or 1/(1-p)) the CUDA step applies to flat element index 0..numel-1 of dropout site `site`
+    (0 encoder output [B*T, D]; 1 attention weights [B, heads, T, T]; 2 attention-block output [B*T, D];
+    3 FFN inner activation [B*T, F]; 4 FFN output [B*T, D])"""
+    if p <= 0:
+        return torch.ones(numel, device=device)
+    key = int(_lowbias32(torch.tensor([(seed * 0x9E3779B9 + site) & 0xFFFFFFFF], dtype=torch.int64))[0])
+    idx = torch.arange(numel, dtype=torch.int64, device=device) & 0xFFFFFFFF
+    keep = _lowbias32(idx ^ key) >= int(p * 4294967296.0)
+    return keep.float() / (1.0 - p)
