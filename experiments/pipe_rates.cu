@@ -60,6 +60,27 @@ __global__ void k(int iters, float a, float b, long long* cyc, float* sink) {
       } else if (OP == 7) {   // FMNMX3
 #pragma unroll
         for (int i = 0; i < CHAINS; ++i) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(x[(i + 1) % CHAINS]), "f"(x[(i + 2) % CHAINS]));
+      } else if (OP == 9) {   // MUFU.EX2.F16 on one half
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) {
+          unsigned short h = (unsigned short)__float_as_uint(x[i]);
+          asm volatile("ex2.approx.f16 %0, %0;" : "+h"(h));
+          x[i] = __uint_as_float((uint32_t)h | 0x30000000u);
+        }
+      } else if (OP == 10) {  // MUFU.EX2.BF16 on one half
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) {
+          unsigned short h = (unsigned short)__float_as_uint(x[i]);
+          asm volatile("ex2.approx.ftz.bf16 %0, %0;" : "+h"(h));
+          x[i] = __uint_as_float((uint32_t)h | 0x30000000u);
+        }
+      } else if (OP == 11) {  // ex2.approx.f16x2: lowers to two MUFU.EX2.F16 + PRMT
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) {
+          uint32_t h = __float_as_uint(x[i]);
+          asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+          x[i] = __uint_as_float(h & 0x3fff3fffu);
+        }
       } else if (OP == 8) {   // the softmax element: FFMA(uniform) + MUFU + FADD + half an F2FP
         float sum = 0.f;
 #pragma unroll
@@ -108,6 +129,9 @@ int main() {
   run<6>("F2FP bf16x2 pack", 4 * CHAINS, cyc, sink);
   run<7>("FMNMX3", 4 * CHAINS, cyc, sink);
   run<8>("softmax element (per element)", 4 * CHAINS, cyc, sink);
+  run<9>("MUFU.EX2.F16 (one half)", 4 * CHAINS, cyc, sink);
+  run<10>("MUFU.EX2.BF16 (one half)", 4 * CHAINS, cyc, sink);
+  run<11>("ex2.approx.f16x2 (per 2 exps)", 4 * CHAINS, cyc, sink);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
