@@ -235,6 +235,12 @@ int32_t w2vseg_head_train_step(w2vseg_handle* h, const float* hidden, int64_t ba
                                float init_dropout, float layer_dropout, uint32_t seed,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- measurement utility ------------------------------------------------------------------------
+ * Effective SM clock: n_blocks single-thread blocks spin for spin_us microseconds of %globaltimer and write
+ * clock64 ticks per microsecond (MHz) to mhz_out[block] (device fp32). Enqueued right after a run of forward
+ * steps it reports the clock the run was held at by the power cap, which nvidia-smi's clocks.sm does not show. */
+int32_t w2vseg_clock_probe(float* mhz_out, int32_t n_blocks, int32_t spin_us, void* stream);
+
 /* ---- talk-level reductions (all device pointers) --------------------------------------------- */
 /* talk[0..n_frames) = NaN, then for each window row w: talk[start[w] .. start[w]+count[w]) =
  * (double) rows[w*row_stride .. +count[w]) ; count[w] < 0 writes zeros over -count[w] frames

@@ -108,3 +108,11 @@ def test_two_handles_same_weights_bit_identical():
         outs.append(p.cpu())
         eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+def test_clock_probe_reports_a_plausible_sm_clock():
+    lib = nat.load()
+    out = torch.zeros(8, device="cuda")
+    nat.check(lib.w2vseg_clock_probe(out.data_ptr(), 8, 30, nat.current_stream_ptr()), "clock_probe")
+    torch.cuda.synchronize()
+    assert ((out > 300) & (out < 3000)).all(), out

@@ -53,6 +53,7 @@ _SZ = C.c_size_t
 # name -> (restype, argtypes); every symbol include/w2vseg.h declares
 SIGNATURES = {
     "w2vseg_abi_version": (_I32, []),
+    "w2vseg_clock_probe": (_I32, [_P, _I32, _I32, _P]),
     "w2vseg_last_error": (C.c_char_p, []),
     "w2vseg_launch_count": (_I64, []),
     "w2vseg_device_ok": (_I32, []),

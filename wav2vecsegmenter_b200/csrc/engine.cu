@@ -901,6 +901,11 @@ int32_t w2vseg_layernorm(const void* in, int32_t in_f32, int64_t rows, int32_t C
   return layernorm_launch(in, in_f32 != 0, rows, C, gamma, beta, eps, act, (bf16*)out, (cudaStream_t)stream);
 }
 
+int32_t w2vseg_clock_probe(float* mhz_out, int32_t n_blocks, int32_t spin_us, void* stream) {
+  W2V_REQUIRE(mhz_out != nullptr && n_blocks > 0 && spin_us > 0 && spin_us <= 10000, "clock_probe: bad argument");
+  return clock_probe_launch(mhz_out, n_blocks, spin_us, (cudaStream_t)stream);
+}
+
 int32_t w2vseg_attention(const void* qkv, int32_t B, int32_t R, int32_t heads, int32_t head_dim,
                          const int32_t* kv_len, float scale, void* ctx, void* stream) {
   W2V_REQUIRE(qkv && kv_len && ctx, "attention: null argument");

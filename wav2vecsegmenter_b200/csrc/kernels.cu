@@ -839,9 +839,31 @@ moving_average_kernel(const double* __restrict__ arr, long long n, int window,
   out[i] = s / (double)cnt;
 }
 
+// Effective SM clock: one thread per block spins for spin_us of %globaltimer and reports clock64 ticks per
+// microsecond. nvidia-smi's clocks.sm keeps showing the maximum while the power cap holds the sustained forward
+// at ~1.55 GHz (profiles/experiments_r02.md); bench.py enqueues this right after its timed region.
+__global__ void clock_probe_kernel(float* __restrict__ mhz_out, int spin_us) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < (unsigned long long)spin_us * 1000ull);
+  const long long c1 = clock64();
+  mhz_out[blockIdx.x] = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));
+}
+
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
+
+int clock_probe_launch(float* mhz_out, int n_blocks, int spin_us, cudaStream_t s) {
+  if (n_blocks <= 0) return 0;
+  clock_probe_kernel<<<n_blocks, 32, 0, s>>>(mhz_out, spin_us);
+  W2V_CHECK_LAUNCH();
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 int window_stats_launch(const float* audio, int64_t audio_stride, const int32_t* sample_len,

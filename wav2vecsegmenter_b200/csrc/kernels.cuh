@@ -63,6 +63,9 @@ int head_final_launch(const float* y, int B, int R, int C, const float* gamma, c
                       float* logits, float* probs, int64_t prob_stride, int row_cols, int flag_col,
                       const int32_t* included, cudaStream_t s);
 
+// effective SM clock in MHz, one value per block (measurement utility, see kernels.cu)
+int clock_probe_launch(float* mhz_out, int n_blocks, int spin_us, cudaStream_t s);
+
 // fused non-causal attention, key-length masked (HF:500-549; torch MHA in lib/models.py:291-300)
 // lse (optional, fp32 [B, heads, R]): per-row log-sum-exp in the log2 domain, for attention_bwd_launch
 // drop (optional, training only): dropout on the attention weights, mask index ((b*heads + h)*R + q)*R + k
