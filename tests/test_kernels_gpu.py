@@ -226,11 +226,12 @@ def test_conv0(lib, R0, lens, case, impl):
     assert err.mean().item() < 2e-3
 
 
-@pytest.mark.parametrize("C,in_f32,act", [(1024, True, 0), (512, False, 0), (512, False, 1), (512, True, 0)])
-def test_layernorm(lib, C, in_f32, act):
+@pytest.mark.parametrize("C,in_f32,act,rows", [(1024, True, 0, 4099), (512, False, 0, 4099), (512, False, 1, 4099),
+                                               (512, True, 0, 4099), (512, False, 1, 23017), (512, False, 0, 7),
+                                               (1024, True, 0, 23017)])
+def test_layernorm(lib, C, in_f32, act, rows):
     from wav2vecsegmenter_b200 import _native as n
 
-    rows = 4099
     g = torch.Generator(device="cuda").manual_seed(C + act)
     x = torch.randn(rows, C, device="cuda", generator=g) * 3 + 1
     if not in_f32:

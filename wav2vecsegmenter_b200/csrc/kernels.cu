@@ -361,6 +361,80 @@ layernorm1024_stream_kernel(const float* in, long long rows,
   }
 }
 
+// LayerNorm(512) (+ GELU) of the bf16 conv-stack activations, persistent like the kernel above: a warp walks rows
+// with a grid stride and always has its next two rows (1 KB each) in flight while it reduces / normalises / stores
+// the current one; its 16 columns are the same for every row, so their gamma / beta live in registers.
+// In place is fine: a row is completely in registers before it is written, and rows are disjoint.
+__device__ __forceinline__ void ln512_load(uint4 (&r)[2], const __nv_bfloat16* in, long long row, int lane) {
+  const uint4* p = reinterpret_cast<const uint4*>(in) + row * 64;
+  r[0] = __ldcs(p + lane);
+  r[1] = __ldcs(p + 32 + lane);
+}
+template <int ACT>
+__global__ void __launch_bounds__(256, 3)
+layernorm512_stream_kernel(const __nv_bfloat16* in, long long rows, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, float eps, __nv_bfloat16* out) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  float g[16], bt[16];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; k += 4) {
+      const int col = (i * 32 + lane) * 8 + k;
+      const float4 a = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 b = *reinterpret_cast<const float4*>(beta + col);
+      g[8 * i + k] = a.x; g[8 * i + k + 1] = a.y; g[8 * i + k + 2] = a.z; g[8 * i + k + 3] = a.w;
+      bt[8 * i + k] = b.x; bt[8 * i + k + 1] = b.y; bt[8 * i + k + 2] = b.z; bt[8 * i + k + 3] = b.w;
+    }
+  uint4 cur[2], nx1[2], nx2[2];
+  if (row < rows) ln512_load(cur, in, row, lane);
+  if (row + nw < rows) ln512_load(nx1, in, row + nw, lane);
+#pragma unroll 1
+  for (; row < rows; row += nw) {
+    if (row + 2 * nw < rows) ln512_load(nx2, in, row + 2 * nw, lane);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+        v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / 512.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / 512.f) + eps);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        y[k] = fmaf((v[8 * i + k] - mean) * rstd, g[8 * i + k], bt[8 * i + k]);
+        if constexpr (ACT == 1) y[k] = gelu_erf(y[k]);
+      }
+      uint4 u;
+      u.x = pack_bf16x2(y[0], y[1]);
+      u.y = pack_bf16x2(y[2], y[3]);
+      u.z = pack_bf16x2(y[4], y[5]);
+      u.w = pack_bf16x2(y[6], y[7]);
+      reinterpret_cast<uint4*>(out)[row * 64 + i * 32 + lane] = u;
+    }
+    cur[0] = nx1[0]; cur[1] = nx1[1];
+    nx1[0] = nx2[0]; nx1[1] = nx2[1];
+  }
+}
+
 // =============================================================================================
 // small data-movement kernels
 // =============================================================================================
@@ -935,7 +1009,16 @@ int layernorm_launch(const void* in, bool in_f32, int64_t rows, int C, const flo
   ProfScope ps(s, act ? "layernorm_gelu" : "layernorm");
 #define W2V_LN(Cv, F32, ACTv)                                                                  \
   layernorm_kernel<Cv, F32, ACTv><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, out)
-  if (C == 512 && !in_f32 && act == 0) W2V_LN(512, false, 0);
+  static const bool ln_v1 = getenv("W2VSEG_LN") != nullptr && strcmp(getenv("W2VSEG_LN"), "v1") == 0;
+  if (C == 512 && !in_f32 && !ln_v1) {
+    const long long want = (rows + 7) / 8;
+    const long long cap = 3LL * num_sms();
+    const unsigned g512 = (unsigned)(want < cap ? want : cap);
+    const __nv_bfloat16* in16 = reinterpret_cast<const __nv_bfloat16*>(in);
+    if (act == 1) layernorm512_stream_kernel<1><<<g512, 256, 0, s>>>(in16, rows, gamma, beta, eps, out);
+    else layernorm512_stream_kernel<0><<<g512, 256, 0, s>>>(in16, rows, gamma, beta, eps, out);
+  }
+  else if (C == 512 && !in_f32 && act == 0) W2V_LN(512, false, 0);
   else if (C == 512 && !in_f32 && act == 1) W2V_LN(512, false, 1);
   else if (C == 512 && in_f32 && act == 0) W2V_LN(512, true, 0);
   else if (C == 1024 && in_f32 && act == 0) {
