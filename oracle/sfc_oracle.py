@@ -113,7 +113,7 @@ def encoder(sd, audio: torch.Tensor, sample_lens, keep_layers: int, n_heads: int
     dtype = audio.dtype
     f = feature_extractor(sd, audio)                                          # HF:1348-1349
     B, T, _ = f.shape
-    valid = torch.zeros(B, T, dtype=torch.bool)                              # HF:1026-1044
+    valid = torch.zeros(B, T, dtype=torch.bool, device=audio.device)        # HF:1026-1044
     for b, n in enumerate(sample_lens):
         valid[b, : conv_out_frames(int(n))] = True
     p = W2V + "feature_projection."
