@@ -421,6 +421,9 @@ def main():
                                                         16000 * 420 + 345, 62, 1, 14),
         "speech_talk_mh_x2": lambda: gold_talk_decisive(ns, "speech_talk_mh_x2", synth.MIDDLE_HALF, 0,
                                                         16000 * 300 + 1234, 63, 2, 14),
+        # configs[0]'s model, middle (0/16) with the frozen encoder (no adapters), on a 260 s talk
+        "speech_talk_middle": lambda: gold_talk_decisive(ns, "speech_talk_middle", synth.MIDDLE, 0,
+                                                         16000 * 260 + 4321, 65, 1, 14),
         # configs[4]: 2 h single stream (360 windows, 359 640 frames): the reference's full yaml for
         # dac / strm / pthr(+moving average); probabilities stored as an every-8th-frame fp32 sample
         "speech_talk_2h": lambda: gold_talk_decisive(ns, "speech_talk_2h", synth.TINY, 0, 16000 * 7200, 64, 1, 14,

@@ -188,11 +188,12 @@ def _decisive_engine(g):
     return eng
 
 
-@pytest.mark.parametrize("name", ["speech_talk_large", "speech_talk_mh_x2"])
+@pytest.mark.parametrize("name", ["speech_talk_large", "speech_talk_mh_x2", "speech_talk_middle"])
 def test_boundaries_identical_headline_configs(name, seg):
     """The same boundary-identity claim on the model configurations BASELINE.json names: large (24/24) +
-    24 adapters over a 420 s talk (one tiling, configs[1]/[2]) and middle+half (8/16) with two overlapped
-    tilings over 300 s (configs[3] as written). Golden boundaries / probabilities: the unmodified reference
+    24 adapters over a 420 s talk (one tiling, configs[1]/[2]), middle+half (8/16) with two overlapped
+    tilings over 300 s (configs[3] as written) and middle (0/16, frozen encoder, no adapters: configs[0]'s
+    model) over 260 s. Golden boundaries / probabilities: the unmodified reference
     pipeline in fp32 on CPU with the calibrated output layer stored in the fixture
     (oracle/make_golden.py:gold_talk_decisive). Asserted per fixture: pSTRM and pTHR(+MA) boundaries >= 99 %
     (98 %) identical, pDAC >= 90 % (see stable_boundaries: the reference's own pDAC output is less stable than
