@@ -183,18 +183,33 @@ colreduce_partial_kernel(const TA* __restrict__ a, long long lda, const float* _
   if (c >= C) return;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = per * blockIdx.y, r1 = min(rows, r0 + per);
-  float s0 = 0.f, s1 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float av;
-    if (mode == 2) av = rowscale[r];
-    else av = (float)a[r * lda + c];
-    if (mode == 0) { s0 += av; continue; }
-    const float2 st = stats[r];
-    s0 = fmaf(av, (x[r * C + c] - st.x) * st.y, s0);
-    s1 += av;
+  // four rows in flight per thread (independent loads), four accumulators combined in a fixed order
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    float av[4], xv[4];
+    float2 st[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      av[u] = mode == 2 ? rowscale[r + u] : (float)a[(r + u) * lda + c];
+      if (mode != 0) { xv[u] = x[(r + u) * C + c]; st[u] = stats[r + u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (mode == 0) { s0[u] += av[u]; continue; }
+      s0[u] = fmaf(av[u], (xv[u] - st[u].x) * st[u].y, s0[u]);
+      s1[u] += av[u];
+    }
   }
-  partial[((long long)blockIdx.y * 2 + 0) * C + c] = s0;
-  partial[((long long)blockIdx.y * 2 + 1) * C + c] = s1;
+  for (; r < r1; ++r) {
+    const float av = mode == 2 ? rowscale[r] : (float)a[r * lda + c];
+    if (mode == 0) { s0[0] += av; continue; }
+    const float2 st = stats[r];
+    s0[0] = fmaf(av, (x[r * C + c] - st.x) * st.y, s0[0]);
+    s1[0] += av;
+  }
+  partial[((long long)blockIdx.y * 2 + 0) * C + c] = (s0[0] + s0[1]) + (s0[2] + s0[3]);
+  partial[((long long)blockIdx.y * 2 + 1) * C + c] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
 }
 __global__ void __launch_bounds__(256)
 colreduce_final_kernel(const float* __restrict__ partial, int C, int slabs, float* __restrict__ out0,
@@ -303,20 +318,30 @@ gather_dropout_kernel(const float* __restrict__ src, long long batch_stride, int
 }
 
 // ---- bf16 transpose with zero padding: dst[c, r] = src[r, c] for r < rows, 0 for rows <= r < rows_pad ------
+// 64 x 64 tiles through shared memory, 16-byte global loads and stores (cols, ld_src multiples of 8; rows_pad a
+// multiple of 64; 16-byte aligned bases — the launcher checks)
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long rows, int cols,
                       __nv_bfloat16* __restrict__ dst, long long rows_pad) {
-  __shared__ __nv_bfloat16 tile[64][66];
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];      // row stride 144 B: 16-byte aligned, conflict-light
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
-    tile[r][c] = (r0 + r < rows && c0 + c < cols) ? src[(r0 + r) * ld_src + c0 + c] : __float2bfloat16_rn(0.f);
+#pragma unroll
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int r = i >> 3, k = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + r < rows && c0 + 8 * k < cols) v = *reinterpret_cast<const uint4*>(src + (r0 + r) * ld_src + c0 + 8 * k);
+    *reinterpret_cast<uint4*>(&tile[r][8 * k]) = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int c = i >> 6, r = i & 63;
-    if (c0 + c < cols && r0 + r < rows_pad) dst[(long long)(c0 + c) * rows_pad + r0 + r] = tile[r][c];
+#pragma unroll
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int c = i & 63, k = i >> 6;                       // consecutive threads: consecutive columns (smem rows
+    if (c0 + c >= cols) continue;                           // read along a column, two threads per bank word)
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = tile[8 * k + e][c];
+    *reinterpret_cast<uint4*>(dst + (long long)(c0 + c) * rows_pad + r0 + 8 * k) = *reinterpret_cast<const uint4*>(o);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -356,7 +381,7 @@ static int colreduce(const void* a, bool a_bf16, int64_t lda, const float* x, co
                      const float* rowscale, int64_t rows, int C, int mode, float* scratch, size_t scratch_floats,
                      float* out0, float* out1, cudaStream_t s) {
   if (rows <= 0 || C <= 0) return 0;
-  int slabs = (int)std::min<long long>(64, (rows + 127) / 128);
+  int slabs = (int)std::min<long long>(256, (rows + 63) / 64);
   slabs = (int)std::min<long long>(slabs, (long long)(scratch_floats / ((size_t)2 * C)));
   W2V_REQUIRE(slabs >= 1, "colreduce: scratch of %zu floats too small for C=%d", scratch_floats, C);
   dim3 grid(blocks_for_t(C, 256), slabs);
@@ -433,6 +458,10 @@ int gather_dropout_launch(const float* src, int64_t batch_stride, int B, int T, 
 int transpose_bf16_launch(const __nv_bfloat16* src, int64_t ld_src, int64_t rows, int cols, __nv_bfloat16* dst,
                           int64_t rows_pad, cudaStream_t s) {
   if (rows_pad <= 0 || cols <= 0) return 0;
+  W2V_REQUIRE(cols % 8 == 0 && ld_src % 8 == 0 && rows_pad % 64 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "transpose: cols %d / ld %lld / rows_pad %lld must be multiples of 8 / 8 / 64, 16-byte aligned", cols,
+              (long long)ld_src, (long long)rows_pad);
   dim3 grid(blocks_for_t(rows_pad, 64), blocks_for_t(cols, 64));
   ProfScope ps(s, "train.transpose");
   transpose_bf16_kernel<<<grid, 256, 0, s>>>(src, ld_src, rows, cols, dst, rows_pad);
