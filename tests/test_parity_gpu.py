@@ -138,6 +138,46 @@ def test_probs_match_oracle_on_seeded_inputs(lens):
     assert T_hidden <= eng.frame_stride(lmax) - 1
 
 
+@pytest.mark.parametrize("spec_name,seed", [("TINY", 11), ("TINY", 12), ("TINY_GN", 13), ("TINY_POSTLN", 14)])
+def test_probs_match_oracle_on_edge_lengths(spec_name, seed):
+    """ragged batches whose lengths sit on the edges the frame arithmetic has: the shortest encodable window
+    (400 samples = 1 frame), one sample either side of a frame boundary of the conv stack (400 + 320 k - 1, + 0,
+    + 1), lengths where the reference's round((n + 1e-6) * 49.95 / 16000) and the conv frame count differ by one
+    (the +-1 fix-up of lib/evaluate.py:63-70), and an all-zero (silent) row, against the oracle on the same inputs"""
+    from oracle import sfc_oracle
+
+    spec = getattr(synth, spec_name)
+    rng = np.random.RandomState(seed)
+    k = int(rng.randint(20, 120))
+    lens = [400 + 320 * k - 1, 400 + 320 * k, 400 + 320 * k + 1, 400, int(rng.randint(500, 30000)),
+            int(rng.randint(30000, 46000))]
+    rng.shuffle(lens)
+    sd = synth.random_state_dict(spec, seed)
+    eng = engine_for(spec, seed)
+    raw = make_batch(lens, 100 + seed)
+    silent = int(rng.randint(0, len(lens)))
+    raw[silent] = 0.0
+    lmax = max(lens)
+    out_len = out_lens_ref(lens)
+    out_mask = torch.zeros(len(lens), max(out_len), dtype=torch.bool)
+    for i, n in enumerate(out_len):
+        out_mask[i, :n] = True
+    included = [bool(raw[i].abs().sum() > 0) for i in range(len(lens))]
+    norm = sfc_oracle.normalize_rows(raw, included)
+    with torch.no_grad():
+        ref_p, _, ref_mask, _ = sfc_oracle.batch_probs(sd, norm, lens, out_mask, spec.keep_layers, spec.head_heads,
+                                                       post_ln=spec.post_ln)
+    ol = ref_mask.sum(1).tolist()
+    _, probs = eng.sfc_forward(raw.cuda(), lens, [lmax] * len(lens), ol, lmax)
+    p = probs[:, : ref_mask.shape[1]].cpu()
+    assert torch.isfinite(p).all()
+    live = [i for i in range(len(lens)) if i != silent]      # the silent row is reported as zeros downstream
+    err = (p[live] - ref_p[live]).abs().max().item()         # (lib/evaluate.py:100-111), its probabilities are unused
+    assert err <= PROB_TOL, (lens, err)
+    for i in live:                                           # nothing leaks past a window's own frames
+        assert (p[i, ol[i]:] == 0).all()
+
+
 def test_window_independent_of_batch_composition():
     """a window's valid-frame probabilities do not depend on what else is in the device batch
     (the property that lets windows shard across GPUs), given the same norm_len"""
