@@ -1,4 +1,6 @@
-"""A/B of the step time (large 24/24 + adapters, 14 x 20 s) with PDL off / on, for the library named by W2VSEG_LIB."""
+"""A/B of the step time (large 24/24 + adapters, 14 x 20 s) with PDL off / on, for the library named by W2VSEG_LIB.
+Needs a library built with experiments/pdl_r02.patch.txt applied (it adds w2vseg_set_pdl); the shipped library does not
+use programmatic dependent launch (profiles/experiments_r02.md: no gain under the power cap)."""
 import os
 import torch
 from wav2vecsegmenter_b200 import synth
