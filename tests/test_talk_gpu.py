@@ -519,3 +519,49 @@ def test_silent_window_reported_as_zero(tiny_engine):
     assert (got[999:1998] == 0).all()
     assert np.abs(got[:999] - ref[:999]).max() < 1e-6 and np.abs(got[1998:] - ref[1998:]).max() < 1e-6
     assert (ref[999:1998] > 0).any()
+
+
+def _oracle_talk(sd, spec, wave_t, segment_sec, inference_times, batch_size):
+    """the whole-talk pipeline assembled from the oracle's pieces (oracle/host_oracle.py + oracle/sfc_oracle.py):
+    window plan, reference batches, CollateFn normalisation, forward, scatter, NaN fill, tiling average"""
+    from oracle import host_oracle as ho
+    from oracle import sfc_oracle
+
+    n = len(wave_t)
+    n_frames = ho.to_outframes(n)
+    per = []
+    for i in range(inference_times):
+        starts, ends = ho.window_plan(n, segment_sec, inference_times, i)
+        talk = np.full(n_frames, np.nan, dtype=np.float64)
+        for b0 in range(0, len(starts), batch_size):
+            ss, ee = starts[b0: b0 + batch_size], ends[b0: b0 + batch_size]
+            fr = [ho.window_frames(s, e) for s, e in zip(ss, ee)]
+            waves = [wave_t[s:e].numpy() for s, e in zip(ss, ee)]
+            c = ho.collate(waves, [f[0] for f in fr], [f[1] for f in fr])
+            audio = sfc_oracle.normalize_rows(torch.from_numpy(c["audio_raw"]), c["included"])
+            with torch.no_grad():
+                p, _, _, shift = sfc_oracle.batch_probs(sd, audio, c["in_len"], torch.from_numpy(c["out_mask"]),
+                                                        spec.keep_layers, spec.head_heads)
+            ho.scatter_batch(talk, p.numpy().astype(np.float64), c["starts"], c["ends"], c["included"], shift)
+        ho.nan_fill(talk)
+        per.append(talk)
+    return ho.average_tilings(per)
+
+
+@pytest.mark.parametrize("segment_sec,inference_times,batch_size", [(7, 2, 5), (30, 3, 2), (13, 1, 3)])
+def test_other_window_lengths_match_oracle_pipeline(tiny_engine, segment_sec, inference_times, batch_size):
+    """`inference_segment_length` is a config key (conf/segment.yaml:13): windows of 7 / 13 / 30 s (349 / 649 /
+    1 499 frames), overlapped tilings and small reference batches, whole-talk path vs the oracle pipeline"""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    n = 16000 * 71 + 3217
+    g = torch.Generator().manual_seed(segment_sec)
+    wave_t = torch.randn(n, generator=g) * (0.03 + 0.3 * torch.rand(n // 8000 + 1, generator=g).repeat_interleave(8000)[:n])
+    sd = synth.random_state_dict(synth.TINY, 0)
+    ref = _oracle_talk(sd, synth.TINY, wave_t, segment_sec, inference_times, batch_size)
+    res = TalkRunner(tiny_engine, batch_size=batch_size, segment_sec=segment_sec,
+                     inference_times=inference_times).run([wave_t.numpy()])[0]
+    assert len(res.probs) == len(ref)
+    assert not np.isnan(res.probs).any()
+    err = np.abs(res.probs - ref).max()
+    assert err <= PROB_TOL, (segment_sec, inference_times, err)
