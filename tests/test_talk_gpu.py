@@ -565,3 +565,17 @@ def test_other_window_lengths_match_oracle_pipeline(tiny_engine, segment_sec, in
     assert not np.isnan(res.probs).any()
     err = np.abs(res.probs - ref).max()
     assert err <= PROB_TOL, (segment_sec, inference_times, err)
+
+
+def test_large_device_batches_are_bit_identical(tiny_engine):
+    """a window's probabilities do not depend on the device batch it travels in — what makes sharding over GPUs
+    reproduce one GPU bit for bit: 2 000 s of audio (100 windows) in device batches of 100, 7 and 1"""
+    from wav2vecsegmenter_b200.pipeline import TalkRunner
+
+    n = 16000 * 2000 + 911
+    g = torch.Generator().manual_seed(5)
+    wave_f = (torch.randn(n, generator=g) * 0.1).numpy()
+    outs = [TalkRunner(tiny_engine, batch_size=14, inference_times=1, device_batch=db).run([wave_f])[0].probs
+            for db in (100, 7, 1)]
+    assert np.isfinite(outs[0]).all() and len(outs[0]) == int(np.round(n * 49.95 / 16000))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
