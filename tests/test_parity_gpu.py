@@ -178,6 +178,43 @@ def test_probs_match_oracle_on_edge_lengths(spec_name, seed):
         assert (p[i, ol[i]:] == 0).all()
 
 
+def test_outlier_channels_in_the_residual_stream():
+    """trained XLS-R checkpoints carry a few residual-stream channels that are orders of magnitude larger than the
+    rest (massive activations). Emulated on the tiny model: three output biases of the first FFN set to +-80 / 150 and
+    one feature-projection bias to 40, so the fp32 residual stream, both LayerNorms after it, the adapters and the
+    head see channels ~100x the typical magnitude. The probabilities must stay within the tolerance of the oracle."""
+    from oracle import sfc_oracle
+    from wav2vecsegmenter_b200.engine import SFCEngine
+
+    spec = synth.TINY
+    sd = synth.random_state_dict(spec, 21)
+    w2v = "wav2vec_model.model."
+    b = sd[w2v + "encoder.layers.0.feed_forward.output_dense.bias"]
+    b[3], b[500], b[777] = 80.0, -80.0, 150.0
+    sd[w2v + "feature_projection.projection.bias"][123] = 40.0
+    lens = [48000, 31000, 40007]
+    raw = make_batch(lens, 78)
+    lmax = max(lens)
+    out_len = out_lens_ref(lens)
+    out_mask = torch.zeros(len(lens), max(out_len), dtype=torch.bool)
+    for i, n in enumerate(out_len):
+        out_mask[i, :n] = True
+    norm = sfc_oracle.normalize_rows(raw, [True] * len(lens))
+    with torch.no_grad():
+        hid = sfc_oracle.encoder(sd, norm, lens, spec.keep_layers)
+        ref_p, _, ref_mask, _ = sfc_oracle.batch_probs(sd, norm, lens, out_mask, spec.keep_layers, spec.head_heads)
+    assert hid.abs().max().item() > 100 * hid.abs().median().item()     # the outliers are really there
+    eng = SFCEngine(spec)
+    eng.load_state_dict(sd)
+    ol = ref_mask.sum(1).tolist()
+    _, probs = eng.sfc_forward(raw.cuda(), lens, [lmax] * len(lens), ol, lmax)
+    p = probs[:, : ref_mask.shape[1]].cpu()
+    err = (p - ref_p).abs().max().item()
+    print(f"OUTLIER max |hidden| {hid.abs().max().item():.1f}, median {hid.abs().median().item():.3f}; max prob err {err:.4f}")
+    eng.close()
+    assert torch.isfinite(p).all() and err <= PROB_TOL, err
+
+
 def test_window_independent_of_batch_composition():
     """a window's valid-frame probabilities do not depend on what else is in the device batch
     (the property that lets windows shard across GPUs), given the same norm_len"""
