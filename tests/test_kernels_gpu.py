@@ -282,3 +282,33 @@ def test_attention(lib, heads, dh, R, lens, impl):
     p = torch.nan_to_num(p, nan=0.0)  # windows with zero valid keys -> zeros
     ref = (p @ v).permute(0, 2, 1, 3).reshape(B * R, D)
     assert (ctx.float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("impl", ["w2vseg_attention", "w2vseg_attention_mma"])
+@pytest.mark.parametrize("heads,dh,R,lens", [(16, 64, 1000, [999, 640]), (8, 128, 700, [700, 333]), (16, 64, 300, [300, 129, 1])])
+def test_attention_sharply_peaked_scores(lib, heads, dh, R, lens, impl):
+    """scores spread over +-35 (q and k scaled by 3: softmax close to an arg-max, the running max moves by more than
+    the lazy-rescale threshold 2^8 many times per row, most probabilities underflow to 0 in bf16) against fp32 torch on
+    the SAME bf16 inputs. (End to end such a regime cannot be compared with an fp32 reference: a 0.4 % bf16 rounding
+    of q / k moves a score of 60 by 0.24, i.e. the attention weights by 27 % — for any bf16 implementation.)"""
+    from wav2vecsegmenter_b200 import _native as n
+
+    B, D = len(lens), heads * dh
+    g = torch.Generator(device="cuda").manual_seed(7 * R + dh)
+    qkv = torch.randn(B * R, 3 * D, device="cuda", generator=g)
+    qkv[:, : 2 * D] *= 3.0
+    qkv = qkv.bfloat16()
+    kv_len = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    ctx = torch.empty(B * R, D, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dh)
+    n.check(getattr(lib, impl)(n.ptr(qkv), B, R, heads, dh, n.ptr(kv_len), scale, n.ptr(ctx), n.current_stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(B, R, 3, heads, dh).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * scale
+    assert s.abs().max().item() > 30
+    mask = torch.arange(R, device="cuda")[None, :] >= kv_len[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * R, D)
+    assert torch.isfinite(ctx.float()).all()
+    assert (ctx.float() - ref).abs().max().item() < 4e-2
